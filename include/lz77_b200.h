@@ -1,0 +1,126 @@
+/*
+ * lz77_b200.h -- C ABI of the B200-native LZ77 codec (liblz77b200.so).
+ *
+ * Drop-in boundary for the hot path of cstdvd/lz77 (citations are file:line
+ * into the reference tree):
+ *
+ *   reference interface                         replaced by
+ *   ------------------------------------------  ---------------------------------
+ *   encode(FILE*, bitFILE*, la, sb) lz77.h:14   lz77_gpu_encode[_device]
+ *     lz77.c:51-140 driving tree.c:62-260
+ *     (insert/find/delete/updateOffset) and
+ *     writecode lz77.c:246-252 -> bitIO_write
+ *     bitio.c:203-239
+ *   decode(bitFILE*, FILE*)        lz77.h:15    lz77_gpu_decode[_device],
+ *     lz77.c:148-197, readcode lz77.c:260-283       lz77_gpu_decode_size[_device]
+ *     -> bitIO_read bitio.c:256-298
+ *   bitof(n)                       bitio.h:25   lz77_bitof / lz77_token_bits
+ *     bitio.c:41-43
+ *   defaults LA 15 / SB 4095       lz77.c:21-22 LZ77_DEFAULT_LA / LZ77_DEFAULT_SB
+ *   limits  -l 2..255, -s 0..65535 main.c:35-38 LZ77_MIN_LA .. LZ77_MAX_SB
+ *
+ * The byte stream is the reference's: a 4-byte header
+ * (SB, LA as uint16 LE; lz77.c:74-75) followed by fixed-width LSB-first tokens
+ * off:bitof(SB) | len:bitof(LA) | next:8 (lz77.c:249-251), zero padded to a
+ * byte (bitio.c:180-182).  The reference decoder decodes what the encoder
+ * here writes; the decoder here decodes what the reference encoder writes.
+ *
+ * Conventions: plain pointers and sizes; the caller owns every buffer; every
+ * entry point returns 0 or a negative LZ77_E_* code and never calls exit();
+ * there is NO CPU fallback -- without a CUDA device every compute entry point
+ * returns LZ77_E_NODEVICE.  One host thread drives one GPU (one process per
+ * GPU for multi-GPU runs); calls are synchronous (the result is complete on
+ * return).  Not re-entrant on the same device from several threads.
+ */
+#ifndef LZ77_B200_H
+#define LZ77_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LZ77_DEFAULT_LA 15    /* lz77.c:21 */
+#define LZ77_DEFAULT_SB 4095  /* lz77.c:22 */
+#define LZ77_MIN_LA 2         /* main.c:35 */
+#define LZ77_MAX_LA 255       /* main.c:36 */
+#define LZ77_MIN_SB 0         /* main.c:37 (0 is accepted by the CLI; see B3) */
+#define LZ77_MAX_SB 65535     /* main.c:38 */
+
+#define LZ77_OK          0
+#define LZ77_E_ARG      (-1)  /* bad parameter (size, sb/la out of range, NULL)   */
+#define LZ77_E_SPACE    (-2)  /* output buffer too small                          */
+#define LZ77_E_STREAM   (-3)  /* malformed stream (short header, sb/la of 0, an   */
+                              /* offset that reaches before the start of output)  */
+#define LZ77_E_NOMEM    (-4)  /* host or device allocation failed                 */
+#define LZ77_E_NODEVICE (-5)  /* no CUDA device / library not initialised         */
+#define LZ77_E_CUDA     (-6)  /* a CUDA call failed; see lz77_gpu_last_error()    */
+
+/* ---- format arithmetic (host only, no device needed) -------------------- */
+
+/* ceil(log2 n), the integer restatement of bitof(), bitio.c:41-43 */
+int  lz77_bitof(int n);
+/* bits per token: bitof(sb) + bitof(la) + 8, lz77.c:249-251 */
+int  lz77_token_bits(int sb, int la);
+/* worst case stream size: header + one token per input byte */
+long lz77_gpu_encode_bound(long n_in, int sb, int la);
+/* size of the independent blocks the encoder cuts the input into: no match
+ * reaches across a multiple of this, and a token starts on every multiple */
+long lz77_gpu_block_size(int sb);
+/* bytes after which the greedy parse restarts inside a block */
+long lz77_gpu_segment_size(void);
+
+/* ---- lifetime ------------------------------------------------------------ */
+
+int  lz77_gpu_device_count(void);
+/* bind the library to one CUDA device (creates its stream and scratch).
+ * Calling it again with another device re-binds. */
+int  lz77_gpu_init(int device);
+void lz77_gpu_shutdown(void);
+const char *lz77_gpu_strerror(int rc);
+const char *lz77_gpu_last_error(void);
+
+/* pinned host memory for fast host<->device copies (optional) */
+void *lz77_gpu_host_alloc(long n);
+void  lz77_gpu_host_free(void *p);
+
+/* ---- host-buffer entry points (what encode()/decode() wrappers call) ---- */
+
+/* sb / la of -1 select the defaults, as in encode(), lz77.c:65-66 */
+int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la,
+                    unsigned char *out, long out_cap, long *n_out);
+int lz77_gpu_decode_size(const unsigned char *in, long n_in, long *n_out);
+int lz77_gpu_decode(const unsigned char *in, long n_in,
+                    unsigned char *out, long out_cap, long *n_out);
+
+/* ---- device-buffer entry points ------------------------------------------
+ * Pointers are device memory on the bound device, 16-byte aligned, with a
+ * capacity that is a multiple of 16 bytes (the kernels move 128-bit words).
+ * The caller must have finished producing d_in before the call. */
+int lz77_gpu_encode_device(const void *d_in, long n_in, int sb, int la,
+                           void *d_out, long out_cap,
+                           long *n_out, long *n_tokens);
+int lz77_gpu_decode_size_device(const void *d_in, long n_in, long *n_out);
+int lz77_gpu_decode_device(const void *d_in, long n_in,
+                           void *d_out, long out_cap, long *n_out);
+
+/* ---- measurement ---------------------------------------------------------
+ * Device time (CUDA events on the library's stream) of each kernel of the
+ * last encode / decode call, in milliseconds, and how many kernels ran. */
+struct lz77_timing {
+    float enc_search_ms;   /* longest-match search + greedy parse           */
+    float enc_scan_ms;     /* token count prefix sums                       */
+    float enc_pack_ms;     /* warp-cooperative bit-packer                   */
+    float dec_scan_ms;     /* token length scan + tile table                */
+    float dec_copy_ms;     /* match-copy / literal tile decode              */
+    float h2d_ms, d2h_ms;  /* host entry points only                        */
+    int   launches;        /* kernels launched by the last call             */
+    long  n_tokens;        /* tokens written / read by the last call        */
+};
+int lz77_gpu_last_timing(struct lz77_timing *t);
+/* per-kernel event timing costs a few synchronisations; 0 turns it off */
+void lz77_gpu_set_timing(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LZ77_B200_H */

@@ -1,0 +1,430 @@
+// capi.cu -- the C ABI of liblz77b200.so (see include/lz77_b200.h).
+//
+// Thin shim between C host code and the sm_100a kernels: parameter checks that
+// mirror the reference CLI (main.c:35-38,102-114), device scratch management,
+// host<->device copies for the host-buffer entry points, CUDA-event timing of
+// every stage.  No CPU implementation of the codec lives here: without a CUDA
+// device every compute entry point fails with LZ77_E_NODEVICE.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/lz77_b200.h"
+#include "kernels.cuh"
+
+using namespace lz77;
+
+namespace {
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    void *scratch = nullptr;
+    size_t scratch_cap = 0;
+    void *stage_in = nullptr;   // device staging for the host entry points
+    size_t stage_in_cap = 0;
+    void *stage_out = nullptr;
+    size_t stage_out_cap = 0;
+    unsigned long long *pinned = nullptr;  // small pinned read-back area
+    cudaEvent_t ev[8];
+    bool timing = true;
+    lz77_timing last;
+    char err[256];
+};
+
+Context g;
+
+int fail_cuda(cudaError_t rc, const char *what)
+{
+    snprintf(g.err, sizeof g.err, "%s: %s", what, cudaGetErrorString(rc));
+    cudaGetLastError();  // clear the sticky-free error
+    if (rc == cudaErrorMemoryAllocation) return LZ77_E_NOMEM;
+    if (rc == cudaErrorNoDevice || rc == cudaErrorInsufficientDriver) return LZ77_E_NODEVICE;
+    return LZ77_E_CUDA;
+}
+
+#define CK(call)                                          \
+    do {                                                  \
+        cudaError_t rc_ = (call);                         \
+        if (rc_ != cudaSuccess) return fail_cuda(rc_, #call); \
+    } while (0)
+
+int grow(void **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return LZ77_OK;
+    if (*buf) {
+        cudaFree(*buf);
+        *buf = nullptr;
+        *cap = 0;
+    }
+    need = (need + (size_t)(1 << 20) - 1) & ~(size_t)((1 << 20) - 1);
+    cudaError_t rc = cudaMalloc(buf, need);
+    if (rc != cudaSuccess) return fail_cuda(rc, "cudaMalloc");
+    *cap = need;
+    return LZ77_OK;
+}
+
+// Resolve and validate (sb, la) the way encode() + main.c do: -1 selects the
+// default (lz77.c:65-66); la in 2..255 and sb in 0..65535 (main.c:35-38).
+// sb == 0 makes the reference divide by zero (tree.c:66) and is
+// rejected here.
+int make_params(int sb, int la, Params *P)
+{
+    if (sb == -1) sb = LZ77_DEFAULT_SB;
+    if (la == -1) la = LZ77_DEFAULT_LA;
+    if (sb < 1 || sb > LZ77_MAX_SB || la < 1 || la > LZ77_MAX_LA) return LZ77_E_ARG;
+    P->sb = sb;
+    P->la = la;
+    P->ob = bitof(sb);
+    P->lb = bitof(la);
+    P->tbits = P->ob + P->lb + 8;
+    int cap = (1 << P->ob) - 1;  // Appendix B2: off == 2^ob does not fit the field
+    P->window = sb < cap ? sb : cap;
+    P->block = lz77_gpu_block_size(sb);
+    P->block_shift = bitof((int)P->block);
+    return LZ77_OK;
+}
+
+float ms_between(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    return ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lz77_bitof(int n) { return bitof(n); }
+
+int lz77_token_bits(int sb, int la) { return bitof(sb) + bitof(la) + 8; }
+
+long lz77_gpu_encode_bound(long n_in, int sb, int la)
+{
+    if (sb == -1) sb = LZ77_DEFAULT_SB;
+    if (la == -1) la = LZ77_DEFAULT_LA;
+    const long t = lz77_token_bits(sb, la);
+    return 4 + (n_in * t + 7) / 8;
+}
+
+long lz77_gpu_block_size(int sb)
+{
+    if (sb == -1) sb = LZ77_DEFAULT_SB;
+    return sb <= 8191 ? 65536L : 131072L;
+}
+
+long lz77_gpu_segment_size(void) { return kSegBytes; }
+
+int lz77_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void lz77_gpu_shutdown(void)
+{
+    if (!g.ready) return;
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    for (auto &e : g.ev) cudaEventDestroy(e);
+    if (g.scratch) cudaFree(g.scratch);
+    if (g.stage_in) cudaFree(g.stage_in);
+    if (g.stage_out) cudaFree(g.stage_out);
+    if (g.pinned) cudaFreeHost(g.pinned);
+    cudaStreamDestroy(g.stream);
+    g = Context();
+}
+
+int lz77_gpu_init(int device)
+{
+    if (g.ready && g.device == device) return LZ77_OK;
+    if (g.ready) lz77_gpu_shutdown();
+    int n = lz77_gpu_device_count();
+    if (n <= 0) {
+        snprintf(g.err, sizeof g.err, "no CUDA device visible");
+        return LZ77_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) return LZ77_E_ARG;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (auto &e : g.ev) CK(cudaEventCreate(&e));
+    CK(cudaMallocHost((void **)&g.pinned, 256));
+    g.device = device;
+    g.ready = true;
+    memset(&g.last, 0, sizeof g.last);
+    return LZ77_OK;
+}
+
+const char *lz77_gpu_strerror(int rc)
+{
+    switch (rc) {
+    case LZ77_OK: return "ok";
+    case LZ77_E_ARG: return "bad argument";
+    case LZ77_E_SPACE: return "output buffer too small";
+    case LZ77_E_STREAM: return "malformed stream";
+    case LZ77_E_NOMEM: return "out of memory";
+    case LZ77_E_NODEVICE: return "no CUDA device / library not initialised";
+    case LZ77_E_CUDA: return "CUDA error";
+    }
+    return "unknown error";
+}
+
+const char *lz77_gpu_last_error(void) { return g.err; }
+
+void *lz77_gpu_host_alloc(long n)
+{
+    void *p = nullptr;
+    if (n <= 0) n = 1;
+    if (cudaMallocHost(&p, (size_t)n) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void lz77_gpu_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void lz77_gpu_set_timing(int enabled) { g.timing = enabled != 0; }
+
+int lz77_gpu_last_timing(struct lz77_timing *t)
+{
+    if (!t) return LZ77_E_ARG;
+    *t = g.last;
+    return LZ77_OK;
+}
+
+// ---------------------------------------------------------------------------
+// encode
+// ---------------------------------------------------------------------------
+
+int lz77_gpu_encode_device(const void *d_in, long n_in, int sb, int la, void *d_out, long out_cap,
+                           long *n_out, long *n_tokens)
+{
+    if (!g.ready) return LZ77_E_NODEVICE;
+    Params P;
+    if (make_params(sb, la, &P) != LZ77_OK || n_in < 0 || !d_out || (n_in > 0 && !d_in) || !n_out)
+        return LZ77_E_ARG;
+    const long bound = lz77_gpu_encode_bound(n_in, P.sb, P.la);
+    if (out_cap < ((bound + 15) & ~15L)) return LZ77_E_SPACE;
+    CK(cudaSetDevice(g.device));
+    int rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in));
+    if (rc) return rc;
+
+    unsigned long long *d_total = nullptr;
+    StageEvents se = {{g.ev[0], g.ev[1], g.ev[2], g.ev[3]}};
+    CK(launch_encode((const uint8_t *)d_in, n_in, P, g.scratch, (uint32_t *)d_out, &d_total,
+                     g.stream, g.timing ? &se : nullptr));
+    CK(cudaMemcpyAsync(g.pinned, d_total, 8, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    const unsigned long long k = g.pinned[0];
+    *n_out = 4 + (long)((k * (unsigned long long)P.tbits + 7) / 8);
+    if (n_tokens) *n_tokens = (long)k;
+
+    memset(&g.last, 0, sizeof g.last);
+    g.last.launches = encode_launch_count(n_in);
+    g.last.n_tokens = (long)k;
+    if (g.timing) {
+        g.last.enc_search_ms = ms_between(g.ev[0], g.ev[1]);
+        g.last.enc_scan_ms = ms_between(g.ev[1], g.ev[2]);
+        g.last.enc_pack_ms = ms_between(g.ev[2], g.ev[3]);
+    }
+    return LZ77_OK;
+}
+
+int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned char *out,
+                    long out_cap, long *n_out)
+{
+    if (!g.ready) return LZ77_E_NODEVICE;
+    Params P;
+    if (make_params(sb, la, &P) != LZ77_OK || n_in < 0 || !out || (n_in > 0 && !in) || !n_out)
+        return LZ77_E_ARG;
+    CK(cudaSetDevice(g.device));
+    const long bound = lz77_gpu_encode_bound(n_in, P.sb, P.la);
+    const size_t in_cap = ((size_t)n_in + 15) & ~(size_t)15;
+    const size_t o_cap = ((size_t)bound + 15) & ~(size_t)15;
+    int rc = grow(&g.stage_in, &g.stage_in_cap, in_cap + 16);
+    if (rc) return rc;
+    rc = grow(&g.stage_out, &g.stage_out_cap, o_cap + 16);
+    if (rc) return rc;
+
+    CK(cudaEventRecord(g.ev[4], g.stream));
+    if (n_in > 0) CK(cudaMemcpyAsync(g.stage_in, in, (size_t)n_in, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaEventRecord(g.ev[5], g.stream));
+    long n = 0, k = 0;
+    rc = lz77_gpu_encode_device(g.stage_in, n_in, P.sb, P.la, g.stage_out, (long)o_cap, &n, &k);
+    if (rc) return rc;
+    if (n > out_cap) return LZ77_E_SPACE;
+    CK(cudaEventRecord(g.ev[6], g.stream));
+    CK(cudaMemcpyAsync(out, g.stage_out, (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev[7], g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    *n_out = n;
+    if (g.timing) {
+        g.last.h2d_ms = ms_between(g.ev[4], g.ev[5]);
+        g.last.d2h_ms = ms_between(g.ev[6], g.ev[7]);
+    }
+    return LZ77_OK;
+}
+
+// ---------------------------------------------------------------------------
+// decode
+// ---------------------------------------------------------------------------
+
+namespace {
+
+// header parse, lz77.c:157-158; the header always travels through the host
+int read_header(const unsigned char hdr[4], long n_in, Params *P, long long *n_tokens)
+{
+    if (n_in < 4) return LZ77_E_STREAM;
+    const int sb = hdr[0] | (hdr[1] << 8);
+    const int la = hdr[2] | (hdr[3] << 8);
+    if (sb < 1 || la < 1 || la > LZ77_MAX_LA) return LZ77_E_STREAM;  // bitof(0) is undefined
+    if (make_params(sb, la, P) != LZ77_OK) return LZ77_E_STREAM;
+    // lz77.c:271-280: a short read ends the stream, so trailing bits < T are padding
+    *n_tokens = ((long long)(n_in - 4) * 8) / P->tbits;
+    return LZ77_OK;
+}
+
+// runs pass 1; on success *n_out is the decoded size
+int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_tokens, long *n_out)
+{
+    if (!g.ready) return LZ77_E_NODEVICE;
+    if (n_in < 0 || !d_in || !n_out) return LZ77_E_ARG;
+    if (n_in < 4) return LZ77_E_STREAM;
+    CK(cudaSetDevice(g.device));
+    unsigned char hdr[4];
+    CK(cudaMemcpyAsync(g.pinned, d_in, 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    memcpy(hdr, g.pinned, 4);
+    int rc = read_header(hdr, n_in, P, n_tokens);
+    if (rc) return rc;
+    memset(&g.last, 0, sizeof g.last);
+    g.last.n_tokens = (long)*n_tokens;
+    if (*n_tokens == 0) {
+        *n_out = 0;
+        return LZ77_OK;
+    }
+    rc = grow(&g.scratch, &g.scratch_cap, decode_scratch_bytes(*n_tokens, *P));
+    if (rc) return rc;
+    DecodeInfo *d_info = nullptr;
+    if (g.timing) CK(cudaEventRecord(g.ev[0], g.stream));
+    CK(launch_decode_scan((const uint32_t *)d_in, n_in, *n_tokens, *P, g.scratch, &d_info,
+                          g.stream));
+    if (g.timing) CK(cudaEventRecord(g.ev[1], g.stream));
+    CK(cudaMemcpyAsync(g.pinned, d_info, sizeof(DecodeInfo), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    const DecodeInfo *info = (const DecodeInfo *)g.pinned;
+    *n_out = (long)info->n_out;
+    g.last.launches = decode_launch_count(false);
+    if (g.timing) g.last.dec_scan_ms = ms_between(g.ev[0], g.ev[1]);
+    return LZ77_OK;
+}
+
+}  // namespace
+
+int lz77_gpu_decode_size_device(const void *d_in, long n_in, long *n_out)
+{
+    Params P;
+    long long k = 0;
+    return decode_scan_device(d_in, n_in, &P, &k, n_out);
+}
+
+int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_cap, long *n_out)
+{
+    Params P;
+    long long k = 0;
+    long n = 0;
+    int rc = decode_scan_device(d_in, n_in, &P, &k, &n);
+    if (rc) return rc;
+    *n_out = n;
+    if (n == 0) return LZ77_OK;
+    if (!d_out) return LZ77_E_ARG;
+    if (out_cap < n) return LZ77_E_SPACE;
+    if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
+    CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, P, g.scratch, (uint8_t *)d_out,
+                          g.stream));
+    if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
+    // the error flag is final only after pass 2
+    DecodeInfo *d_info = (DecodeInfo *)g.scratch;
+    CK(cudaMemcpyAsync(g.pinned, d_info, sizeof(DecodeInfo), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.last.launches = decode_launch_count(true);
+    if (g.timing) g.last.dec_copy_ms = ms_between(g.ev[2], g.ev[3]);
+    if (((const DecodeInfo *)g.pinned)->error) return LZ77_E_STREAM;
+    return LZ77_OK;
+}
+
+int lz77_gpu_decode_size(const unsigned char *in, long n_in, long *n_out)
+{
+    if (!g.ready) return LZ77_E_NODEVICE;
+    if (n_in < 0 || !in || !n_out) return LZ77_E_ARG;
+    if (n_in < 4) return LZ77_E_STREAM;
+    CK(cudaSetDevice(g.device));
+    const size_t in_cap = ((size_t)n_in + 15) & ~(size_t)15;
+    int rc = grow(&g.stage_in, &g.stage_in_cap, in_cap + 16);
+    if (rc) return rc;
+    CK(cudaMemsetAsync((char *)g.stage_in + (in_cap - 16), 0, 32, g.stream));
+    CK(cudaMemcpyAsync(g.stage_in, in, (size_t)n_in, cudaMemcpyHostToDevice, g.stream));
+    return lz77_gpu_decode_size_device(g.stage_in, n_in, n_out);
+}
+
+int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long out_cap,
+                    long *n_out)
+{
+    if (!g.ready) return LZ77_E_NODEVICE;
+    if (n_in < 0 || !in || !n_out) return LZ77_E_ARG;
+    if (n_in < 4) return LZ77_E_STREAM;
+    CK(cudaSetDevice(g.device));
+    const size_t in_cap = ((size_t)n_in + 15) & ~(size_t)15;
+    int rc = grow(&g.stage_in, &g.stage_in_cap, in_cap + 16);
+    if (rc) return rc;
+    CK(cudaEventRecord(g.ev[4], g.stream));
+    CK(cudaMemsetAsync((char *)g.stage_in + (in_cap - 16), 0, 32, g.stream));
+    CK(cudaMemcpyAsync(g.stage_in, in, (size_t)n_in, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaEventRecord(g.ev[5], g.stream));
+
+    Params P;
+    long long k = 0;
+    long n = 0;
+    rc = decode_scan_device(g.stage_in, n_in, &P, &k, &n);
+    if (rc) return rc;
+    const float scan_ms = g.last.dec_scan_ms;
+    *n_out = n;
+    if (n == 0) return LZ77_OK;
+    if (!out) return LZ77_E_ARG;
+    if (out_cap < n) return LZ77_E_SPACE;
+    rc = grow(&g.stage_out, &g.stage_out_cap, (((size_t)n + 15) & ~(size_t)15) + 16);
+    if (rc) return rc;
+    if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
+    CK(launch_decode_copy((const uint32_t *)g.stage_in, n_in, k, n, P, g.scratch,
+                          (uint8_t *)g.stage_out, g.stream));
+    if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
+    CK(cudaMemcpyAsync(g.pinned, g.scratch, sizeof(DecodeInfo), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev[6], g.stream));
+    CK(cudaMemcpyAsync(out, g.stage_out, (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaEventRecord(g.ev[7], g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.last.launches = decode_launch_count(true);
+    g.last.dec_scan_ms = scan_ms;
+    if (g.timing) {
+        g.last.dec_copy_ms = ms_between(g.ev[2], g.ev[3]);
+        g.last.h2d_ms = ms_between(g.ev[4], g.ev[5]);
+        g.last.d2h_ms = ms_between(g.ev[6], g.ev[7]);
+    }
+    if (((const DecodeInfo *)g.pinned)->error) return LZ77_E_STREAM;
+    return LZ77_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// common.cuh -- shared definitions of the sm_100a LZ77 kernels.
+//
+// Wire format (reference lz77.c:74-75, 246-252; bitio.c:203-239): the stream
+// is one little-endian bit string; token k sits at bit 32 + k*T and holds
+//   off : OB = bitof(SB) bits | len : LB = bitof(LA) bits | next : 8 bits
+// LSB first.  OB <= 16 and LB <= 8, so a token always fits one 32-bit value
+//   tok = off | len << OB | next << (OB + LB).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lz77 {
+
+constexpr int kSegBytes = 2048;        // greedy parse restarts every segment
+constexpr int kHeaderBits = 32;        // SB:16, LA:16 (lz77.c:74-75)
+
+struct Params {
+    int sb, la;        // header values
+    int ob, lb, tbits; // field widths, token width
+    int window;        // usable search reach: min(sb, 2^ob - 1)  (Appendix B2)
+    long long block;   // independent block size in bytes (power of two)
+    int block_shift;
+};
+
+__host__ __device__ inline int bitof(int n)  // bitio.c:41-43 in integers
+{
+    int b = 0;
+    if (n <= 1) return 0;
+    while ((1L << b) < (long)n) b++;
+    return b;
+}
+
+// ---- unaligned little-endian helpers ------------------------------------
+
+// 32 bits starting at bit `bit` of a word array (guarded at the end)
+__device__ __forceinline__ uint32_t load_bits32(const uint32_t *__restrict__ words,
+                                                long long n_words, long long bit)
+{
+    long long w = bit >> 5;
+    int s = (int)(bit & 31);
+    uint32_t lo = (w < n_words) ? __ldg(words + w) : 0u;
+    uint32_t hi = (s != 0 && w + 1 < n_words) ? __ldg(words + w + 1) : 0u;
+    return __funnelshift_r(lo, hi, s);
+}
+
+// 4 bytes at an arbitrary shared-memory byte index (reads two aligned words)
+__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t *smem, int idx)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (idx & ~3));
+    return __funnelshift_r(w[0], w[1], (idx & 3) * 8);
+}
+
+// exact per-byte zero detector: bit 7 of every byte of the result is set iff
+// that byte of x is zero
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
+{
+    return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+}
+
+// ---- mbarrier / TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_commit_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// make generic-proxy shared-memory writes visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+}  // namespace lz77

@@ -1,0 +1,461 @@
+// decode.cu -- token-parallel LZ77 decoder kernels for sm_100a.
+//
+// Replaces lz77.c:148-197 (decode loop), lz77.c:260-283 (readcode) and
+// bitio.c:256-298 (bit-at-a-time reader).  Tokens are fixed width, so token k
+// sits at bit 32 + k*T and output offsets are a prefix sum of len+1 -- there is
+// no serial bitstream parse.
+//
+//   pass 1  lz77_decode_scan_kernel   one pass over the tokens (decoupled
+//           look-back prefix sum): decoded size, and for every output tile the
+//           token that contains its first byte.
+//   pass 2  lz77_decode_tile_kernel   one CTA per output tile: the tile is
+//           assembled in shared memory with one lane per token (literal store +
+//           ascending match copy, lz77.c:178-194) and written to HBM with
+//           128-bit stores.  Match sources inside the tile are read from shared
+//           memory behind an in-order commit frontier; sources in earlier tiles
+//           (streams the reference encoder wrote reach back SB bytes from
+//           anywhere) are read from HBM once that tile has been published.
+//           Streams of the block-parallel encoder never leave their tile
+//           (tile == encoder block), so every tile decodes independently.
+#include "kernels.cuh"
+
+namespace lz77 {
+
+// ---------------------------------------------------------------------------
+// pass 1: token length scan
+// ---------------------------------------------------------------------------
+
+constexpr int kDsThreads = 256;
+constexpr int kDsRows = 16;                          // tokens per lane
+constexpr int kDsChunk = kDsThreads * kDsRows;       // tokens per CTA
+constexpr unsigned long long kFlagAgg = 1ull << 62;  // chunk aggregate published
+constexpr unsigned long long kFlagInc = 2ull << 62;  // inclusive prefix published
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+struct DecodeScratch {
+    unsigned long long *status;  // look-back state per scan chunk
+    long long *tile_tok;         // token containing the first byte of tile j
+    long long *tile_pos;         // output position of that token
+    unsigned int *tile_done;     // tile j has been written to HBM
+    unsigned int *tickets;       // [0] scan chunk ticket, [1] tile ticket
+    DecodeInfo *info;
+    size_t zero_bytes;           // leading part that must be zeroed per call
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__global__ void __launch_bounds__(kDsThreads)
+lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
+                        Params P, int tile_shift, unsigned long long *status,
+                        long long *__restrict__ tile_tok, long long *__restrict__ tile_pos,
+                        unsigned int *tickets, DecodeInfo *info)
+{
+    __shared__ long long s_chunk;
+    __shared__ unsigned long long s_warp_tot[kDsThreads / 32];
+    __shared__ unsigned long long s_prefix;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&tickets[0], 1u);  // chunks start in order
+    __syncthreads();
+    const long long c = s_chunk;
+    const long long warp_base = c * kDsChunk + (long long)warp * (32 * kDsRows);
+    const uint32_t len_mask = (1u << P.lb) - 1u;
+
+    // per lane: inclusive scan of len+1 over this warp's 512 tokens
+    uint32_t incl[kDsRows];
+    uint32_t L[kDsRows];
+    uint32_t carry = 0;
+#pragma unroll
+    for (int r = 0; r < kDsRows; r++) {
+        const long long k = warp_base + r * 32 + lane;
+        uint32_t l1 = 0;
+        if (k < n_tokens) {
+            const uint32_t tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
+            l1 = ((tok >> P.ob) & len_mask) + 1u;
+        }
+        L[r] = l1;
+        uint32_t x = l1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += t;
+        }
+        incl[r] = carry + x;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0) s_warp_tot[warp] = carry;
+    __syncthreads();
+
+    unsigned long long warp_off = 0, chunk_total = 0;
+#pragma unroll
+    for (int w = 0; w < kDsThreads / 32; w++) {
+        const unsigned long long t = s_warp_tot[w];
+        if (w < warp) warp_off += t;
+        chunk_total += t;
+    }
+
+    // decoupled look-back: warp 0 resolves this chunk's exclusive prefix
+    if (warp == 0) {
+        unsigned long long exclusive = 0;
+        if (c > 0) {
+            if (lane == 0) atomicExch(&status[c], kFlagAgg | chunk_total);
+            long long idx = c - 1 - lane;
+            while (true) {
+                unsigned long long s = idx >= 0 ? ld_volatile_u64(&status[idx]) : kFlagInc;
+                while (__any_sync(0xffffffffu, (s >> 62) == 0)) {
+                    if ((s >> 62) == 0) s = ld_volatile_u64(&status[idx]);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+                const unsigned long long val = s & kValMask;
+                if (inc_mask) {
+                    const int first = __ffs(inc_mask) - 1;
+                    exclusive += warp_sum_u64(lane <= first ? val : 0ull);
+                    break;
+                }
+                exclusive += warp_sum_u64(val);
+                idx -= 32;
+            }
+        }
+        if (lane == 0) {
+            atomicExch(&status[c], kFlagInc | (exclusive + chunk_total));
+            s_prefix = exclusive;
+        }
+    }
+    __syncthreads();
+    const unsigned long long base_pos = s_prefix + warp_off;
+
+    // tile table: the token that covers byte j << tile_shift
+    const long long tile_bytes = 1LL << tile_shift;
+#pragma unroll
+    for (int r = 0; r < kDsRows; r++) {
+        const long long k = warp_base + r * 32 + lane;
+        if (k >= n_tokens) continue;
+        const long long pos = (long long)(base_pos + incl[r] - L[r]);
+        const long long j = (pos + tile_bytes - 1) >> tile_shift;
+        if ((j << tile_shift) < pos + (long long)L[r]) {
+            tile_tok[j] = k;
+            tile_pos[j] = pos;
+        }
+        if (k == n_tokens - 1) info->n_out = (unsigned long long)(pos + L[r]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass 2: tile decode
+// ---------------------------------------------------------------------------
+
+template <int kThreads>
+__device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_t *s_warp,
+                                                             uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = lane < kThreads / 32 ? s_warp[lane] : 0u;
+        uint32_t sinc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, sinc, d);
+            if (lane >= d) sinc += t;
+        }
+        s_warp[lane] = sinc - s;
+        if (lane == 31) *total = sinc;
+    }
+    __syncthreads();
+    const uint32_t r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
+lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
+                        Params P, int tile_shift, const long long *__restrict__ tile_tok,
+                        const long long *__restrict__ tile_pos, long long n_tiles,
+                        long long n_out, uint8_t *out, unsigned int *tile_done,
+                        unsigned int *tickets, DecodeInfo *info)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int kWarps = kThreads / 32;
+    const int tile_bytes = 1 << tile_shift;
+    uint8_t *tile = smem;
+    uint32_t *gpos = reinterpret_cast<uint32_t *>(smem + tile_bytes);  // group start offsets
+
+    __shared__ long long s_tile;
+    __shared__ volatile int s_frontier;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t off_mask = (1u << P.ob) - 1u;
+    const uint32_t len_mask = (1u << P.lb) - 1u;
+    const int lit_shift = P.ob + P.lb;
+
+    while (true) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&tickets[1], 1u);  // tiles start in order
+        __syncthreads();
+        const long long j = s_tile;
+        if (j >= n_tiles) break;
+
+        const long long tile_lo = j << tile_shift;
+        long long tile_hi = tile_lo + tile_bytes;
+        if (tile_hi > n_out) tile_hi = n_out;
+        const int tile_len = (int)(tile_hi - tile_lo);
+        const long long k0 = tile_tok[j];
+        const int p0_rel = (int)(tile_pos[j] - tile_lo);  // <= 0: a token may straddle in
+        long long k_end = n_tokens;
+        if (j + 1 < n_tiles) k_end = tile_tok[j + 1] + (tile_pos[j + 1] < tile_hi ? 1 : 0);
+        const int n_tok = (int)(k_end - k0);
+        const int n_groups = (n_tok + 31) >> 5;
+
+        // ---- phase 1: output offset of every group of 32 tokens -----------
+        for (int g = warp; g < n_groups; g += kWarps) {
+            const long long k = k0 + g * 32 + lane;
+            uint32_t l1 = 0;
+            if (k < k_end) {
+                const uint32_t tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
+                l1 = ((tok >> P.ob) & len_mask) + 1u;
+            }
+            l1 = __reduce_add_sync(0xffffffffu, l1);
+            if (lane == 0) gpos[g] = l1;
+        }
+        __syncthreads();
+        {
+            const int per = (n_groups + kThreads - 1) / kThreads;
+            const int b = threadIdx.x * per;
+            uint32_t s = 0;
+            for (int i = 0; i < per; i++)
+                if (b + i < n_groups) s += gpos[b + i];
+            uint32_t run = block_exclusive_scan_u32<kThreads>(s, s_warp, &s_total);
+            for (int i = 0; i < per; i++) {
+                if (b + i < n_groups) {
+                    const uint32_t v = gpos[b + i];
+                    gpos[b + i] = run;
+                    run += v;
+                }
+            }
+            if (threadIdx.x == 0) s_frontier = p0_rel;
+        }
+        __syncthreads();
+
+        // ---- phase 2: groups in order, one lane per token ------------------
+        for (int g = warp; g < n_groups; g += kWarps) {
+            const long long k = k0 + g * 32 + lane;
+            const bool valid = k < k_end;
+            uint32_t tok = 0;
+            if (valid) tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
+            const int off = (int)(tok & off_mask);
+            const int len = (int)((tok >> P.ob) & len_mask);
+            const uint32_t lit = (tok >> lit_shift) & 0xffu;
+            const int l1 = valid ? len + 1 : 0;
+            int inc = l1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += t;
+            }
+            const int gs_rel = p0_rel + (int)gpos[g];
+            const int ge_rel = gs_rel + __shfl_sync(0xffffffffu, inc, 31);
+            const int pos_rel = gs_rel + inc - l1;
+
+            if (valid) {  // literal, lz77.c:189-194
+                const int d = pos_rel + len;
+                if (d >= 0 && d < tile_len) tile[d] = (uint8_t)lit;
+            }
+            bool pending = valid && len > 0;
+            if (pending && (off == 0 || (long long)off > tile_lo + pos_rel)) {
+                info->error = 1;  // source before the start of the output
+                pending = false;
+            }
+            const int s_rel = pos_rel - off;           // first source byte
+            const int e_rel = s_rel + min(len, off);   // one past the last distinct source byte
+            unsigned int ta = 0, tb = 0;
+            bool ext = pending && s_rel < 0;           // reaches into earlier tiles
+            if (ext) {
+                ta = (unsigned int)((tile_lo + s_rel) >> tile_shift);
+                tb = (unsigned int)((tile_lo + min(e_rel, 0) - 1) >> tile_shift);
+            }
+            __syncwarp();
+
+            while (true) {
+                const unsigned um = __ballot_sync(0xffffffffu, pending);
+                if (!um) break;
+                const int F = s_frontier;
+                const int pfirst = __shfl_sync(0xffffffffu, pos_rel, __ffs(um) - 1);
+                const int Fl = (F >= gs_rel) ? pfirst : F;  // bytes below Fl are final
+                bool ready = pending && (e_rel <= 0 || e_rel <= Fl);
+                if (ready && ext) {
+                    ready = ld_acquire_u32(&tile_done[ta]) != 0u &&
+                            ld_acquire_u32(&tile_done[tb]) != 0u;
+                    if (ready) ext = false;
+                }
+                if (ready) {  // ascending byte copy, lz77.c:178-188
+                    int r = 0;
+                    for (int i = 0; i < len; i++) {
+                        const int a = s_rel + r;
+                        const uint8_t c = a >= 0 ? tile[a] : __ldcg(out + (tile_lo + a));
+                        const int d = pos_rel + i;
+                        if (d >= 0 && d < tile_len) tile[d] = c;
+                        if (++r == off) r = 0;
+                    }
+                    pending = false;
+                }
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, ready)) __nanosleep(40);
+            }
+            if (lane == 0) {
+                while (s_frontier != gs_rel) __nanosleep(20);
+                __threadfence_block();
+                s_frontier = ge_rel;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- flush the tile with 128-bit stores -----------------------------
+        {
+            uint8_t *dst = out + tile_lo;
+            const int n16 = tile_len & ~15;
+            for (int i = threadIdx.x * 16; i < n16; i += kThreads * 16)
+                *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(tile + i);
+            for (int i = n16 + threadIdx.x; i < tile_len; i += kThreads) dst[i] = tile[i];
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_u32(&tile_done[j], 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+
+int decode_tile_bytes(const Params &P)
+{
+    return (int)P.block;  // tile == encoder block: its own streams never leave a tile
+}
+
+static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+static DecodeScratch carve_decode(void *scratch, long long n_tokens, const Params &P)
+{
+    const int tile_shift = P.block_shift;
+    const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
+    const long long max_out = n_tokens << P.lb;  // len + 1 <= 2^lb
+    const long long max_tiles = (max_out >> tile_shift) + 2;
+    char *p = (char *)scratch;
+    DecodeScratch s;
+    s.info = (DecodeInfo *)p;
+    p += 256;
+    s.tickets = (unsigned int *)p;
+    p += 256;
+    s.status = (unsigned long long *)p;
+    p += al256((size_t)n_chunks * 8);
+    s.tile_done = (unsigned int *)p;
+    p += al256((size_t)max_tiles * 4);
+    s.zero_bytes = (size_t)(p - (char *)scratch);
+    s.tile_tok = (long long *)p;
+    p += al256((size_t)max_tiles * 8);
+    s.tile_pos = (long long *)p;
+    p += al256((size_t)max_tiles * 8);
+    return s;
+}
+
+size_t decode_scratch_bytes(long long n_tokens, const Params &P)
+{
+    const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
+    const long long max_tiles = ((n_tokens << P.lb) >> P.block_shift) + 2;
+    return 512 + al256((size_t)n_chunks * 8) + al256((size_t)max_tiles * 4) +
+           2 * al256((size_t)max_tiles * 8) + 1024;
+}
+
+int decode_launch_count(bool with_copy) { return with_copy ? 2 : 1; }
+
+cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
+                               long long n_tokens, const Params &P, void *scratch,
+                               DecodeInfo **d_info, cudaStream_t st)
+{
+    DecodeScratch s = carve_decode(scratch, n_tokens, P);
+    *d_info = s.info;
+    cudaError_t rc = cudaMemsetAsync(scratch, 0, s.zero_bytes, st);
+    if (rc != cudaSuccess) return rc;
+    const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
+    const long long n_words = (n_in_bytes + 3) / 4;
+    if (n_chunks > 0)
+        lz77_decode_scan_kernel<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(
+            d_in_words, n_words, n_tokens, P, P.block_shift, s.status, s.tile_tok, s.tile_pos,
+            s.tickets, s.info);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
+                               long long n_tokens, long long n_out, const Params &P,
+                               void *scratch, uint8_t *d_out, cudaStream_t st)
+{
+    DecodeScratch s = carve_decode(scratch, n_tokens, P);
+    const int tile_shift = P.block_shift;
+    const long long tile_bytes = 1LL << tile_shift;
+    const long long n_tiles = (n_out + tile_bytes - 1) >> tile_shift;
+    const long long n_words = (n_in_bytes + 3) / 4;
+    if (n_tiles == 0) return cudaSuccess;
+    const size_t smem = (size_t)tile_bytes + ((size_t)(tile_bytes >> 5) + 8) * 4;
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (tile_bytes <= 65536) {
+        auto kern = lz77_decode_tile_kernel<512, 3>;
+        cudaError_t rc =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return rc;
+        long long grid = (long long)sms * 3;
+        if (grid > n_tiles) grid = n_tiles;
+        kern<<<(unsigned)grid, 512, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
+                                                 s.tile_tok, s.tile_pos, n_tiles, n_out, d_out,
+                                                 s.tile_done, s.tickets, s.info);
+    } else {
+        auto kern = lz77_decode_tile_kernel<1024, 1>;
+        cudaError_t rc =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return rc;
+        long long grid = sms;
+        if (grid > n_tiles) grid = n_tiles;
+        kern<<<(unsigned)grid, 1024, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
+                                                  s.tile_tok, s.tile_pos, n_tiles, n_out, d_out,
+                                                  s.tile_done, s.tickets, s.info);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace lz77

@@ -1,0 +1,462 @@
+// encode.cu -- block-parallel LZ77 encoder kernels for sm_100a.
+//
+// Replaces, for a batch of independent blocks at once:
+//   tree.c:62-260 (BST insert/find/delete/updateOffset)  -> shared-memory
+//       windowed warp search (lz77_parse_kernel)
+//   lz77.c:89-135 (greedy token loop, match() lz77.c:209-224) -> one warp per
+//       parse segment, sequential in the segment, parallel across segments
+//   lz77.c:246-252 writecode + bitio.c:203-239 bitIO_write -> warp-cooperative
+//       bit-packer (lz77_pack_kernel)
+//
+// The result is the stream oracle/lz77_oracle.c:lz77o_blocked_encode() defines,
+// byte for byte: inside a block the longest match (<= min(LA, bytes left in the
+// segment) - 1) against the last min(window, position in block) bytes, nearest
+// offset among the longest, then a literal.
+#include "kernels.cuh"
+
+namespace lz77 {
+
+// ---------------------------------------------------------------------------
+// K1: longest-match search + greedy parse
+// ---------------------------------------------------------------------------
+//
+// One CTA stages `hist` history bytes + nwarps*kSegBytes input bytes into
+// shared memory with one TMA bulk copy; warp w then parses segment w.  For every
+// token the warp scans the window nearest-first in 512-byte chunks: each lane
+// takes one 16-byte group (LDS.128), filters the 16 candidate starts on the
+// first target byte with an exact SWAR zero-byte test, verifies survivors
+// against the target held in registers, and the (length, nearest start) pair is
+// reduced warp-wide with REDUX.  A chunk that yields a maximum-length match
+// ends the scan early.
+
+template <bool kSmallLA>
+__device__ __forceinline__ int match_len(const uint8_t *smem, int q, int p0,
+                                         const uint32_t (&tgt)[4], int max_len)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (q & ~3));
+    const int sh = (q & 3) * 8;
+    if (kSmallLA) {  // LA <= 16: target in registers, at most 4 words
+        uint32_t a0 = w[0], a1 = w[1];
+        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+        int l;
+        if (x) {
+            l = (__ffs(x) - 1) >> 3;
+        } else {
+            uint32_t a2 = w[2];
+            x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+            if (x) {
+                l = 4 + ((__ffs(x) - 1) >> 3);
+            } else {
+                uint32_t a3 = w[3];
+                x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+                if (x) {
+                    l = 8 + ((__ffs(x) - 1) >> 3);
+                } else {
+                    uint32_t a4 = w[4];
+                    x = __funnelshift_r(a3, a4, sh) ^ tgt[3];
+                    l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
+                }
+            }
+        }
+        return min(l, max_len);
+    } else {
+        int l = 0;
+        uint32_t a = w[0];
+        int wi = 1;
+        while (l < max_len) {
+            uint32_t b = w[wi++];
+            uint32_t x = __funnelshift_r(a, b, sh) ^ lds_u32_unaligned(smem, p0 + l);
+            if (x) {
+                l += (__ffs(x) - 1) >> 3;
+                break;
+            }
+            l += 4;
+            a = b;
+        }
+        return min(l, max_len);
+    }
+}
+
+template <bool kSmallLA>
+__global__ void __launch_bounds__(1024, 1)
+lz77_parse_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
+                  uint32_t *__restrict__ tok_tmp, uint32_t *__restrict__ seg_ntok)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const long long tile_bytes = (long long)nwarps * kSegBytes;
+    const long long tile_lo = (long long)blockIdx.x * tile_bytes;
+    const long long blk_lo = (tile_lo >> P.block_shift) << P.block_shift;
+
+    // ---- stage history + tile -------------------------------------------
+    long long hist = tile_lo - blk_lo;
+    if (hist > P.window) hist = P.window;
+    const int hist_al = (int)((hist + 15) & ~15LL);  // <= tile_lo - blk_lo (both multiples of 16)
+    const long long src_lo = tile_lo - hist_al;
+    long long src_hi = tile_lo + tile_bytes;
+    if (src_hi > n) src_hi = n;
+    const int bytes = (int)(src_hi - src_lo);
+    const int bulk = bytes & ~15;
+    const int dst0 = hist_cap - hist_al;  // smem index of global byte src_lo
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bulk > 0) {
+        mbar_expect_tx(&mbar, (uint32_t)bulk);
+        tma_load_1d(smem + dst0, in + src_lo, (uint32_t)bulk, &mbar);
+    }
+    // ragged tail (< 16 bytes) and zero padding behind the data
+    for (int i = bulk + threadIdx.x; i < bytes + 64; i += blockDim.x)
+        smem[dst0 + i] = (i < bytes) ? in[src_lo + i] : (uint8_t)0;
+    if (bulk > 0) mbar_wait(&mbar, 0);
+    __syncthreads();
+
+    // ---- parse this warp's segment ---------------------------------------
+    const long long seg_lo = tile_lo + (long long)warp * kSegBytes;
+    const long long sgm = (long long)blockIdx.x * nwarps + warp;  // global segment index
+    if (seg_lo >= n) return;
+    long long seg_hi = seg_lo + kSegBytes;
+    if (seg_hi > n) seg_hi = n;
+
+    const int seg_end = (int)(seg_hi - src_lo) + dst0;  // smem index one past the segment
+    int p0 = (int)(seg_lo - src_lo) + dst0;             // smem index of the parse position
+    const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // smem index of the block start (may be < 0)
+    uint32_t *tok_out = tok_tmp + sgm * kSegBytes;
+    const int len_shift = P.ob, lit_shift = P.ob + P.lb;
+
+    int ntok = 0;
+    uint32_t held = 0;  // lane l holds token (ntok & ~31) + l until the row is flushed
+
+    while (p0 < seg_end) {
+        const int max_len = min(P.la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
+        const int reach = min(p0 - blk_idx, P.window);    // lz77.c:101-105
+        uint32_t key = 0;                                 // best (len << 20 | start index)
+
+        if (max_len > 0 && reach > 0) {
+            const int lo_idx = p0 - reach;
+            uint32_t tgt[4] = {0, 0, 0, 0};
+            if (kSmallLA) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) tgt[i] = lds_u32_unaligned(smem, p0 + 4 * i);
+            }
+            const uint32_t b0x4 = (uint32_t)smem[p0] * 0x01010101u;
+            int best_len = 0, best_q = 0;
+
+            for (int base = ((p0 + 15) & ~15) - 512; base + 512 > lo_idx; base -= 512) {
+                const int g = base + lane * 16;
+                if (g + 16 > lo_idx && g < p0) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(smem + g);
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 3; i >= 0; i--) {
+                        uint32_t m = zero_bytes(wv[i] ^ b0x4);
+                        while (m) {
+                            const int bit = 31 - __clz(m);
+                            m ^= 1u << bit;
+                            const int q = g + 4 * i + (bit >> 3);
+                            if (q >= lo_idx && q < p0) {
+                                // farther than anything this lane has seen: must be longer
+                                const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
+                                if (l > best_len) {
+                                    best_len = l;
+                                    best_q = q;
+                                }
+                            }
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, best_len >= max_len)) break;
+            }
+            key = __reduce_max_sync(0xffffffffu,
+                                    best_len ? ((uint32_t)best_len << 20) | (uint32_t)best_q : 0u);
+        }
+
+        const int len = (int)(key >> 20);
+        const int off = len ? p0 - (int)(key & 0xfffffu) : 0;
+        const uint32_t lit = smem[p0 + len];
+        const uint32_t tok = (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
+
+        if (lane == (ntok & 31)) held = tok;
+        ntok++;
+        if ((ntok & 31) == 0) tok_out[ntok - 32 + lane] = held;  // coalesced 128 B row
+        p0 += len + 1;
+    }
+    if (lane < (ntok & 31)) tok_out[(ntok & ~31) + lane] = held;
+    if (lane == 0) seg_ntok[sgm] = (uint32_t)ntok;
+}
+
+// ---------------------------------------------------------------------------
+// token-count prefix sums (uint32 counts -> uint64 exclusive prefix)
+// ---------------------------------------------------------------------------
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v,
+                                                                   unsigned long long *total)
+{
+    __shared__ unsigned long long warp_sums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        unsigned long long s = lane < nw ? warp_sums[lane] : 0ull;
+        unsigned long long sinc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, sinc, d);
+            if (lane >= d) sinc += t;
+        }
+        warp_sums[lane] = sinc - s;  // exclusive warp offsets
+        if (lane == 31) *total = sinc;
+    }
+    __syncthreads();
+    unsigned long long r = warp_sums[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_partial_kernel(const uint32_t *__restrict__ in, long long n,
+                    unsigned long long *__restrict__ partial)
+{
+    __shared__ unsigned long long total;
+    const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++)
+        if (base + i < n) s += in[base + i];
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_top_kernel(unsigned long long *__restrict__ partial, long long n_partial,
+                unsigned long long *__restrict__ grand_total)
+{
+    __shared__ unsigned long long total;
+    unsigned long long carry = 0;
+    for (long long base = 0; base < n_partial; base += blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const unsigned long long v = i < n_partial ? partial[i] : 0ull;
+        const unsigned long long ex = block_exclusive_scan(v, &total);
+        if (i < n_partial) partial[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const uint32_t *__restrict__ in, long long n,
+                  const unsigned long long *__restrict__ partial,
+                  unsigned long long *__restrict__ out)
+{
+    __shared__ unsigned long long total;
+    const long long base = (long long)blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        v[i] = base + i < n ? in[base + i] : 0u;
+        s += v[i];
+    }
+    unsigned long long run = partial[blockIdx.x] + block_exclusive_scan(s, &total);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: warp-cooperative bit-packer
+// ---------------------------------------------------------------------------
+//
+// Segment s owns stream bits [32 + T*prefix[s], 32 + T*(prefix[s] + ntok[s])).
+// 32-bit words that lie fully inside that range are assembled in registers
+// from the <= 5 tokens that overlap them and stored (four at a time as one
+// 128-bit store when the lane's group is interior and 16-byte aligned); the
+// first and last word of a segment may be shared with its neighbours and are
+// OR-ed into words lz77_pack_prepare_kernel zeroed.
+
+__device__ __forceinline__ uint32_t gather_word(const uint32_t *__restrict__ toks, int n_tok,
+                                                long long rel_lo, int tbits)
+{
+    // rel_lo: bit offset of the word relative to the segment's first token bit
+    int t0 = rel_lo <= 0 ? 0 : (int)(rel_lo / tbits);
+    int t1 = (int)((rel_lo + 31) / tbits);
+    if (t1 > n_tok - 1) t1 = n_tok - 1;
+    uint32_t val = 0;
+    for (int t = t0; t <= t1; t++) {
+        const int tb = (int)((long long)t * tbits - rel_lo);  // in (-tbits, 32)
+        const uint32_t v = __ldg(toks + t);
+        val |= tb >= 0 ? v << tb : v >> (-tb);
+    }
+    return val;
+}
+
+__global__ void lz77_pack_prepare_kernel(const uint32_t *__restrict__ seg_ntok,
+                                         const unsigned long long *__restrict__ prefix,
+                                         long long n_seg, Params P, uint32_t *__restrict__ out)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) out[0] = (uint32_t)P.sb | ((uint32_t)P.la << 16);  // lz77.c:74-75
+    if (s >= n_seg) return;
+    const uint32_t nt = seg_ntok[s];
+    if (!nt) return;
+    const long long b0 = kHeaderBits + (long long)P.tbits * (long long)prefix[s];
+    const long long b1 = b0 + (long long)P.tbits * nt;
+    out[b0 >> 5] = 0;
+    out[(b1 - 1) >> 5] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+lz77_pack_kernel(const uint32_t *__restrict__ tok_tmp, const uint32_t *__restrict__ seg_ntok,
+                 const unsigned long long *__restrict__ prefix, long long n_seg, Params P,
+                 uint32_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n_seg) return;
+    const int nt = (int)seg_ntok[s];
+    if (!nt) return;
+    const uint32_t *toks = tok_tmp + s * kSegBytes;
+    const int T = P.tbits;
+    const long long b0 = kHeaderBits + (long long)T * (long long)prefix[s];
+    const long long b1 = b0 + (long long)T * nt;
+    const long long w_first = b0 >> 5, w_last = (b1 - 1) >> 5;
+
+    // groups of four words, aligned to 16 bytes
+    for (long long w4 = (w_first & ~3LL) + 4LL * lane; w4 <= w_last; w4 += 128) {
+        const bool interior = (w4 << 5) >= b0 && ((w4 + 4) << 5) <= b1;
+        if (interior) {
+            uint4 v;
+            v.x = gather_word(toks, nt, ((w4 + 0) << 5) - b0, T);
+            v.y = gather_word(toks, nt, ((w4 + 1) << 5) - b0, T);
+            v.z = gather_word(toks, nt, ((w4 + 2) << 5) - b0, T);
+            v.w = gather_word(toks, nt, ((w4 + 3) << 5) - b0, T);
+            *reinterpret_cast<uint4 *>(out + w4) = v;  // coalesced 128-bit store
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const long long w = w4 + i;
+                if (w < w_first || w > w_last) continue;
+                const uint32_t val = gather_word(toks, nt, (w << 5) - b0, T);
+                if ((w << 5) >= b0 && ((w + 1) << 5) <= b1)
+                    out[w] = val;
+                else
+                    atomicOr(out + w, val);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+
+size_t encode_scratch_bytes(long long n_in)
+{
+    const long long n_seg = (n_in + kSegBytes - 1) / kSegBytes;
+    const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
+    size_t b = 0;
+    b += (size_t)(n_seg * kSegBytes) * sizeof(uint32_t);          // tok_tmp
+    b += (size_t)((n_seg + 63) & ~63LL) * sizeof(uint32_t);       // seg_ntok
+    b += (size_t)((n_seg + 63) & ~63LL) * sizeof(unsigned long long);  // prefix
+    b += (size_t)((n_part + 63) & ~63LL) * sizeof(unsigned long long); // partials
+    b += 256;                                                      // grand total
+    return b + 1024;
+}
+
+static inline char *carve(char *&p, size_t bytes)
+{
+    char *r = p;
+    p += (bytes + 255) & ~(size_t)255;
+    return r;
+}
+
+int encode_parse_config(const Params &P, int *nwarps, int *hist_cap, size_t *smem)
+{
+    *hist_cap = (P.window + 15) & ~15;
+    *nwarps = P.window <= 8191 ? 8 : 32;
+    *smem = (size_t)*hist_cap + (size_t)*nwarps * kSegBytes + 128;
+    return 0;
+}
+
+cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, void *scratch,
+                          uint32_t *d_out_words, unsigned long long **d_total_tokens,
+                          cudaStream_t st, StageEvents *ev)
+{
+    const long long n_seg = (n_in + kSegBytes - 1) / kSegBytes;
+    const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
+    char *p = (char *)scratch;
+    uint32_t *tok_tmp = (uint32_t *)carve(p, (size_t)(n_seg * kSegBytes) * sizeof(uint32_t));
+    uint32_t *seg_ntok = (uint32_t *)carve(p, (size_t)n_seg * sizeof(uint32_t));
+    unsigned long long *prefix =
+        (unsigned long long *)carve(p, (size_t)n_seg * sizeof(unsigned long long));
+    unsigned long long *partial =
+        (unsigned long long *)carve(p, (size_t)n_part * sizeof(unsigned long long));
+    unsigned long long *total = (unsigned long long *)carve(p, 8);
+    *d_total_tokens = total;
+
+    int nwarps, hist_cap;
+    size_t smem;
+    encode_parse_config(P, &nwarps, &hist_cap, &smem);
+    const long long tile_bytes = (long long)nwarps * kSegBytes;
+    const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
+    const bool small_la = P.la <= 16;
+
+    if (ev) cudaEventRecord(ev->e[0], st);
+    if (n_tiles > 0) {
+        auto kern = small_la ? lz77_parse_kernel<true> : lz77_parse_kernel<false>;
+        cudaError_t rc =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return rc;
+        kern<<<(unsigned)n_tiles, nwarps * 32, smem, st>>>(d_in, n_in, P, hist_cap, tok_tmp,
+                                                            seg_ntok);
+    }
+    if (ev) cudaEventRecord(ev->e[1], st);
+    if (n_seg > 0) {
+        scan_partial_kernel<<<(unsigned)n_part, kScanThreads, 0, st>>>(seg_ntok, n_seg, partial);
+        scan_top_kernel<<<1, 1024, 0, st>>>(partial, n_part, total);
+        scan_apply_kernel<<<(unsigned)n_part, kScanThreads, 0, st>>>(seg_ntok, n_seg, partial,
+                                                                      prefix);
+    } else {
+        cudaMemsetAsync(total, 0, 8, st);
+    }
+    if (ev) cudaEventRecord(ev->e[2], st);
+    {
+        const long long nthreads = n_seg > 0 ? n_seg : 1;
+        lz77_pack_prepare_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(
+            seg_ntok, prefix, n_seg, P, d_out_words);
+        if (n_seg > 0)
+            lz77_pack_kernel<<<(unsigned)((n_seg + 7) / 8), 256, 0, st>>>(
+                tok_tmp, seg_ntok, prefix, n_seg, P, d_out_words);
+    }
+    if (ev) cudaEventRecord(ev->e[3], st);
+    return cudaGetLastError();
+}
+
+int encode_launch_count(long long n_in)
+{
+    if (n_in <= 0) return 1;
+    return 6;  // parse, 3 x scan, pack-prepare, pack
+}
+
+}  // namespace lz77

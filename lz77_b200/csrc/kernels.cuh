@@ -1,0 +1,40 @@
+// kernels.cuh -- launch interface between the C ABI (capi.cu) and the kernels.
+#pragma once
+
+#include "common.cuh"
+
+namespace lz77 {
+
+struct StageEvents {
+    cudaEvent_t e[4];
+};
+
+// ---- encoder (encode.cu) ---------------------------------------------------
+size_t encode_scratch_bytes(long long n_in);
+int encode_launch_count(long long n_in);
+// d_out_words must hold 4 + ceil(n_in * T / 8) bytes rounded up to 16.
+// *d_total_tokens receives a device pointer (inside scratch) to the token count.
+cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, void *scratch,
+                          uint32_t *d_out_words, unsigned long long **d_total_tokens,
+                          cudaStream_t st, StageEvents *ev);
+
+// ---- decoder (decode.cu) ---------------------------------------------------
+struct DecodeInfo {            // lives in device scratch, copied back by the C ABI
+    unsigned long long n_out;  // decoded size
+    unsigned int error;        // != 0: malformed stream (bad offset)
+    unsigned int pad;
+};
+
+int decode_tile_bytes(const Params &P);
+size_t decode_scratch_bytes(long long n_tokens, const Params &P);
+int decode_launch_count(bool with_copy);
+// pass 1: token lengths -> decoded size + tile table
+cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
+                               long long n_tokens, const Params &P, void *scratch,
+                               DecodeInfo **d_info, cudaStream_t st);
+// pass 2: tile decode (needs the decoded size pass 1 produced)
+cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
+                               long long n_tokens, long long n_out, const Params &P,
+                               void *scratch, uint8_t *d_out, cudaStream_t st);
+
+}  // namespace lz77

@@ -79,6 +79,9 @@ class Oracle:
         lib.lz77o_blocked_encode.argtypes = [p8, C.c_long, C.c_int, C.c_int, C.c_long,
                                              p8, C.c_long, C.POINTER(C.c_long)]
         lib.lz77o_blocked_encode.restype = C.c_long
+        lib.lz77o_segmented_encode.argtypes = [p8, C.c_long, C.c_int, C.c_int, C.c_long,
+                                               C.c_long, p8, C.c_long, C.POINTER(C.c_long)]
+        lib.lz77o_segmented_encode.restype = C.c_long
         lib.lz77o_unpack_tokens.argtypes = [p8, C.c_long, C.POINTER(C.c_int),
                                             C.POINTER(C.c_int), C.POINTER(C.c_int32),
                                             C.POINTER(C.c_int32), p8, C.c_long]
@@ -120,17 +123,20 @@ class Oracle:
             raise ValueError(f"lz77o_decode size mismatch: {m} != {n}")
         return out[:n].tobytes()
 
-    def blocked_encode(self, data, sb: int = -1, la: int = -1, block: int = 0):
+    def blocked_encode(self, data, sb: int = -1, la: int = -1, block: int = 0,
+                       segment: int = 0):
+        """Specification of the GPU encoder (block-independent windows, parse
+        restart every ``segment`` bytes); returns (stream, token count)."""
         src = _u8(data)
         esb = 4095 if sb == -1 else sb
         ela = 15 if la == -1 else la
         cap = self.encode_bound(src.size, max(esb, 1), max(ela, 1)) + 8
         out = np.zeros(cap, dtype=np.uint8)
         ntok = C.c_long(0)
-        n = self.lib.lz77o_blocked_encode(self._ptr(src), src.size, sb, la, block,
-                                          self._ptr(out), cap, C.byref(ntok))
+        n = self.lib.lz77o_segmented_encode(self._ptr(src), src.size, sb, la, block, segment,
+                                            self._ptr(out), cap, C.byref(ntok))
         if n < 0:
-            raise ValueError(f"lz77o_blocked_encode failed: {n}")
+            raise ValueError(f"lz77o_segmented_encode failed: {n}")
         return out[:n].tobytes(), ntok.value
 
     def unpack_tokens(self, stream):

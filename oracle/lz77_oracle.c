@@ -507,9 +507,9 @@ static void longest_match(const uint8_t *blk, long p, long reach, int max_len,
     *m_len = best;
 }
 
-long lz77o_blocked_encode(const uint8_t *in, long n_in, int sb, int la,
-                          long block, uint8_t *out, long out_cap,
-                          long *n_tokens)
+long lz77o_segmented_encode(const uint8_t *in, long n_in, int sb, int la,
+                            long block, long segment, uint8_t *out,
+                            long out_cap, long *n_tokens)
 {
     const int SB = (sb == -1) ? LZ77O_DEFAULT_SB : sb;
     const int LA = (la == -1) ? LZ77O_DEFAULT_LA : la;
@@ -517,6 +517,10 @@ long lz77o_blocked_encode(const uint8_t *in, long n_in, int sb, int la,
         return LZ77O_E_ARG;
     if (block <= 0)
         block = n_in > 0 ? n_in : 1;
+    if (segment <= 0 || segment > block)
+        segment = block;
+    if (block % segment != 0)
+        return LZ77O_E_ARG;
 
     const int off_bits = lz77o_bitof(SB);
     const int len_bits = lz77o_bitof(LA);
@@ -537,7 +541,12 @@ long lz77o_blocked_encode(const uint8_t *in, long n_in, int sb, int la,
         long nb = n_in - base < block ? n_in - base : block;
         long p = 0;
         while (p < nb) {
-            long left = nb - p;
+            /* the greedy parse restarts at every segment: a token never runs
+             * past the end of its segment (and so never past its block) */
+            long seg_end = (p / segment + 1) * segment;
+            if (seg_end > nb)
+                seg_end = nb;
+            long left = seg_end - p;
             /* lz77.c:87,134 + tree.c:136: len <= min(LA, left) - 1 */
             int max_len = (int)((left < LA ? left : LA) - 1);
             long reach = p < window ? p : window; /* lz77.c:101-105 */
@@ -555,4 +564,12 @@ long lz77o_blocked_encode(const uint8_t *in, long n_in, int sb, int la,
     if (sink.overflow)
         return LZ77O_E_SPACE;
     return (sink.bitpos + 7) >> 3;
+}
+
+long lz77o_blocked_encode(const uint8_t *in, long n_in, int sb, int la,
+                          long block, uint8_t *out, long out_cap,
+                          long *n_tokens)
+{
+    return lz77o_segmented_encode(in, n_in, sb, la, block, 0, out, out_cap,
+                                  n_tokens);
 }

@@ -74,6 +74,18 @@ long lz77o_blocked_encode(const uint8_t *in, long n_in, int sb, int la,
                           long *n_tokens);
 
 /*
+ * The exact stream the GPU encoder writes: as lz77o_blocked_encode, and in
+ * addition the greedy parse restarts every `segment` bytes inside a block (a
+ * token never runs past the end of its segment; the match WINDOW still spans
+ * the whole block).  segment must divide block; segment <= 0 means no restarts.
+ * The GPU encoder uses block = lz77_gpu_block_size(sb), segment =
+ * lz77_gpu_segment_size(); parity with it is byte-for-byte.
+ */
+long lz77o_segmented_encode(const uint8_t *in, long n_in, int sb, int la,
+                            long block, long segment, uint8_t *out,
+                            long out_cap, long *n_tokens);
+
+/*
  * Unpack a stream into token arrays (each of capacity cap, any may be NULL).
  * Returns the token count (which may exceed cap; only cap are stored) or <0.
  */

@@ -1,0 +1,199 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C ABI of
+liblz77b200.so and is checked against the CPU oracle / the committed golden
+streams of the compiled reference."""
+import hashlib
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from _cases import GOLDEN_CASES, PARAM_SETS, case_input
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parents[1]
+GOLDEN_DIR = ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def lz():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (they never fall back to the CPU)")
+    import lz77_b200
+    lz77_b200.init(0)
+    return lz77_b200
+
+
+def _spec(orc, lz, data, sb, la):
+    esb = 4095 if sb == -1 else sb
+    return orc.blocked_encode(data, sb, la, lz.block_size(esb), lz.segment_size())
+
+
+SMALL_INPUTS = [
+    ("empty", b""),
+    ("one", b"a"),
+    ("two", b"ab"),
+    ("abc", b"abcabcabcabcX"),
+    ("a100", b"a" * 100),
+    ("la_minus1", b"xyz" * 4 + b"q"),
+    ("range256x16", bytes(range(256)) * 16),
+]
+
+
+@pytest.mark.parametrize("sb,la", PARAM_SETS)
+@pytest.mark.parametrize("name,data", SMALL_INPUTS, ids=[n for n, _ in SMALL_INPUTS])
+def test_small_inputs_bit_exact(lz, orc, sb, la, name, data):
+    enc = lz.encode(data, la=la, sb=sb)
+    spec, ntok = _spec(orc, lz, data, sb, la)
+    assert enc == spec
+    assert orc.decode(enc) == data          # the reference decoder restatement
+    assert lz.decode(enc) == data           # GPU decoder on its own stream
+    if sb != 4096:  # the reference itself corrupts power-of-two SB (Appendix B2)
+        assert lz.decode(orc.ref_encode(data, sb, la)) == data
+
+
+@pytest.mark.parametrize("sb,la", PARAM_SETS)
+@pytest.mark.parametrize("kind,n", [("zipf_text", 70_001), ("random", 9_000), ("zeros", 10_000),
+                                    ("log_like", 150_000), ("zipf_text", 2048), ("zipf_text", 2049),
+                                    ("zipf_text", 65536), ("zipf_text", 65537), ("zipf_text", 131_071)])
+def test_encode_equals_specification(lz, orc, sb, la, kind, n):
+    """GPU encoder == oracle specification, byte for byte; decodes through the
+    reference decoder restatement."""
+    from lz77_b200 import synth
+    data = synth.make(kind, n, seed=5).numpy().tobytes()
+    enc = lz.encode(data, la=la, sb=sb)
+    spec, ntok = _spec(orc, lz, data, sb, la)
+    assert len(enc) == len(spec)
+    assert enc == spec
+    assert enc[:4] == bytes([sb & 255, sb >> 8, la & 255, la >> 8])
+    assert orc.decode(enc) == data
+    assert lz.decode(enc) == data
+
+
+@pytest.mark.parametrize("case", [c for c in GOLDEN_CASES if c.get("store")],
+                         ids=lambda c: c["name"])
+def test_decode_reference_streams(lz, golden, case):
+    """Streams the compiled reference wrote (tests/golden/streams) decode to
+    the original input."""
+    g = golden[case["name"]]
+    stream = (GOLDEN_DIR / g["stream"]).read_bytes()
+    assert hashlib.sha256(stream).hexdigest() == g["sha256"]
+    data = case_input(case)
+    assert lz.decode_size(stream) == len(data)
+    assert lz.decode(stream) == data
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (65535, 255), (1000, 20), (15, 8)])
+def test_decode_restated_reference_encoder(lz, orc, sb, la):
+    """Unblocked streams (matches reach back SB bytes across every tile
+    boundary) produced by the byte-identical restatement of the reference
+    encoder."""
+    from lz77_b200 import synth
+    for kind, n in (("zipf_text", 400_000), ("log_like", 300_000), ("random", 150_000)):
+        data = synth.make(kind, n, seed=9).numpy().tobytes()
+        stream = orc.ref_encode(data, sb, la)
+        assert lz.decode(stream) == data, (kind, sb, la)
+
+
+def test_known_answer_vectors_decode(lz, golden):
+    for g in golden.values():
+        if "hex" in g and g["ref_roundtrip_ok"]:
+            case = next(c for c in GOLDEN_CASES if c["name"] == g["name"])
+            assert lz.decode(bytes.fromhex(g["hex"])) == case_input(case)
+
+
+def test_zeros_1mib_config1(lz, orc):
+    """BASELINE.json configs[0]: 1 MiB of zeros, default parameters."""
+    data = bytes(1 << 20)
+    enc = lz.encode(data)
+    spec, _ = _spec(orc, lz, data, -1, -1)
+    assert enc == spec
+    assert orc.decode(enc) == data
+    ref_stream = orc.ref_encode(data)
+    assert hashlib.sha256(ref_stream).hexdigest() == \
+        "42e454e313f95e04daa9717687ab77d9ab6351c691bb1fccad1ff73269e5c4b1"
+    assert lz.decode(ref_stream) == data
+
+
+def test_malformed_streams(lz):
+    from lz77_b200 import Lz77Error
+    with pytest.raises(Lz77Error):
+        lz.decode(b"\xff\x0f")                                   # short header
+    with pytest.raises(Lz77Error):
+        lz.decode(b"\x00\x00\x0f\x00")                           # SB == 0
+    with pytest.raises(Lz77Error):
+        lz.decode(b"\xff\x0f\x0f\x00" + bytes([5, 0x10, 65]))    # offset before start
+    assert lz.decode(b"\xff\x0f\x0f\x00") == b""
+    assert lz.decode(b"\xff\x0f\x0f\x00\x00\x00\x61\x00\x00") == b"a"   # padding < one token
+    with pytest.raises(Lz77Error):
+        lz.encode(b"abc", sb=0)
+    with pytest.raises(Lz77Error):
+        lz.encode(b"abc", la=256)
+
+
+@pytest.mark.parametrize("kind,sb,la,n", [("zipf_text", 4095, 15, 64 << 20),
+                                          ("random", 65535, 255, 32 << 20),
+                                          ("log_like", 4095, 15, 64 << 20),
+                                          ("mixed", 65535, 255, 48 << 20)])
+def test_device_roundtrip_large(lz, orc, kind, sb, la, n):
+    """Size-independent properties at tens of MiB: device encode -> device decode
+    is the identity, the stream size equals header + tokens * T, and a slice of
+    whole blocks re-encoded alone gives the same tokens (block independence)."""
+    import torch
+    from lz77_b200 import synth
+    if kind == "mixed":
+        src = synth.mixed(n, seed=3, device="cuda", segment=8 << 20)
+    else:
+        src = synth.make(kind, n, seed=3, device="cuda")
+    stream, ntok = lz.encode_tensor(src, la=la, sb=sb)
+    T = lz.token_bits(sb, la)
+    assert stream.numel() == 4 + (ntok * T + 7) // 8
+    assert lz.decode_size_tensor(stream) == n
+    back = lz.decode_tensor(stream)
+    assert torch.equal(back, src)
+    # the reference decoder restatement agrees on the first 4 MiB worth of blocks
+    B = lz.block_size(sb)
+    head = src[:4 << 20].contiguous()
+    s_head, k_head = lz.encode_tensor(head, la=la, sb=sb)
+    assert torch.equal(s_head[4:4 + (k_head * T) // 8], stream[4:4 + (k_head * T) // 8])
+    assert orc.decode(s_head.cpu().numpy().tobytes()) == head.cpu().numpy().tobytes()
+    assert (4 << 20) % B == 0
+
+
+def test_cli_cross_roundtrip_with_reference(lz, orc, tmp_path):
+    """The C command-line program against the compiled reference binary, both
+    directions (skipped when oracle/_ref/lz77 was not shipped)."""
+    from lz77_b200 import synth
+    from oracle import ref_binary
+    cli = ROOT / "lz77_b200" / "bin" / "lz77"
+    assert cli.exists(), "lz77_b200/bin/lz77 is not built"
+    data = synth.zipf_text(500_000, seed=21).numpy().tobytes()
+    fin = tmp_path / "in.bin"
+    fin.write_bytes(data)
+    for args in ([], ["-s", "65535", "-l", "255"], ["-s", "1000", "-l", "20"]):
+        ours = tmp_path / "ours.lz"
+        subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(ours), *args], check=True)
+        back = tmp_path / "back.bin"
+        subprocess.run([str(cli), "-d", "-i", str(ours), "-o", str(back)], check=True)
+        assert back.read_bytes() == data
+        assert orc.decode(ours.read_bytes()) == data
+        ref = ref_binary()
+        if ref is not None:
+            rback = tmp_path / "rback.bin"
+            subprocess.run([str(ref), "-d", "-i", str(ours), "-o", str(rback)], check=True)
+            assert rback.read_bytes() == data
+            theirs = tmp_path / "theirs.lz"
+            subprocess.run([str(ref), "-c", "-i", str(fin), "-o", str(theirs), *args], check=True)
+            subprocess.run([str(cli), "-d", "-i", str(theirs), "-o", str(back)], check=True)
+            assert back.read_bytes() == data
+    # usage errors keep the reference's messages and exit code
+    r = subprocess.run([str(cli), "-c", "-o", "x"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Input file must be provided" in r.stderr
+    r = subprocess.run([str(cli), "-i", str(fin), "-o", "x"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Select ENCODE or DECODE mode" in r.stderr
+    r = subprocess.run([str(cli), "-c", "-i", str(fin), "-o", "x", "-l", "1"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Bad lookahead size value." in r.stderr
