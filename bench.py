@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LZ77 hot path (BASELINE.json metric:
+"encode+decode GB/s at 1/2/4/8 B200; ratio; CPU ref GB/s same run").
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
+
+Workload (N = 1 and per rank for N > 1, weak scaling): BASELINE.json configs[1],
+256 MiB of seeded synthetic Zipf text, -s 4095 -l 15.  One step = one encode of
+the whole input followed by one decode of the stream that encode produced.
+
+  value   uncompressed GB/s of the encode+decode roundtrip, all ranks together,
+          inputs and outputs resident in HBM (device entry points of the C ABI),
+          timed with CUDA events on the stream the kernels run on, max over ranks
+  e2e     the same roundtrip through the host-buffer entry points of the C ABI
+          (lz77_gpu_encode / lz77_gpu_decode, what the reference-shaped
+          encode()/decode() wrappers call) from pinned host buffers: H2D of the
+          input and D2H of the result inside the timed region, every step
+  roofline      the dominant kernel (longest-match search) against measured HBM
+  roofline_decode  the decode match-copy kernel (the north_star's 70 % target)
+  cpu_baseline  the compiled reference (oracle/_ref/lz77) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = dict(name="configs[1]: 256 MiB synthetic Zipf text, -s 4095 -l 15",
+                kind="zipf_text", n=256 << 20, sb=4095, la=15, seed=1234)
+METRIC = "encode+decode GB/s"
+UNIT = "GB/s"
+
+
+# --------------------------------------------------------------------------- #
+# helpers
+# --------------------------------------------------------------------------- #
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- #
+# CPU reference arm
+# --------------------------------------------------------------------------- #
+
+def _ref_roundtrip(args):
+    """Encode + decode one slice with the compiled reference CLI (or the oracle
+    port when the binary did not travel); returns (bytes, compressed bytes)."""
+    path, use_binary = args
+    if use_binary:
+        exe = str(ROOT / "oracle" / "_ref" / "lz77")
+        subprocess.run([exe, "-c", "-i", path, "-o", path + ".lz"], check=True,
+                       capture_output=True)
+        subprocess.run([exe, "-d", "-i", path + ".lz", "-o", path + ".out"], check=True,
+                       capture_output=True)
+        n, c = os.path.getsize(path), os.path.getsize(path + ".lz")
+        ok = open(path, "rb").read() == open(path + ".out", "rb").read()
+    else:
+        from oracle import oracle
+        orc = oracle()
+        data = open(path, "rb").read()
+        enc = orc.ref_encode(data, WORKLOAD["sb"], WORKLOAD["la"])
+        ok = orc.decode(enc) == data
+        n, c = len(data), len(enc)
+    if not ok:
+        raise RuntimeError("CPU reference roundtrip mismatch")
+    return n, c
+
+
+class CpuReference:
+    """The reference's own CPU implementation of the path on all host cores:
+    one independent single-threaded process per core, each on its own slice of
+    the workload (the reference has no threading of its own)."""
+
+    def __init__(self, slice_bytes: int):
+        from oracle import build_oracle, ref_binary
+        from lz77_b200 import synth
+        build_oracle()
+        self.use_binary = ref_binary() is not None
+        self.kind = "reference" if self.use_binary else "port"
+        self.cores = os.cpu_count() or 1
+        self.slice_bytes = slice_bytes
+        tmp = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        self.dir = tempfile.TemporaryDirectory(dir=tmp)
+        data = synth.make(WORKLOAD["kind"], slice_bytes * self.cores, seed=WORKLOAD["seed"],
+                          device="cpu").numpy()
+        self.paths = []
+        for i in range(self.cores):
+            p = os.path.join(self.dir.name, f"slice{i}")
+            data[i * slice_bytes:(i + 1) * slice_bytes].tofile(p)
+            self.paths.append(p)
+
+    def step(self):
+        """one bounded sample: every core encodes + decodes its slice; returns
+        (seconds, bytes, compressed bytes)"""
+        from concurrent.futures import ThreadPoolExecutor
+        t0 = time.perf_counter()
+        if self.use_binary:
+            with ThreadPoolExecutor(self.cores) as ex:   # threads only wait on subprocesses
+                res = list(ex.map(_ref_roundtrip, [(p, True) for p in self.paths]))
+        else:
+            from concurrent.futures import ProcessPoolExecutor
+            with ProcessPoolExecutor(self.cores) as ex:
+                res = list(ex.map(_ref_roundtrip, [(p, False) for p in self.paths]))
+        dt = time.perf_counter() - t0
+        return dt, sum(r[0] for r in res), sum(r[1] for r in res)
+
+    def sample_desc(self):
+        return (f"{self.cores} x {self.slice_bytes >> 20} MiB slices of the Zipf-text workload, "
+                f"one single-threaded {'oracle/_ref/lz77' if self.use_binary else 'oracle port'} "
+                f"process per core, encode+decode, files on tmpfs")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ref = CpuReference(slice_bytes=args.ref_slice_mib << 20)
+    for _ in range(args.warmup):
+        ref.step()
+    total_t, total_b, total_c = 0.0, 0, 0
+    for _ in range(args.steps):
+        dt, b, c = ref.step()
+        total_t += dt
+        total_b += b
+        total_c += c
+    value = total_b / total_t / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_t / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD["name"], "sb": WORKLOAD["sb"], "la": WORKLOAD["la"],
+                   "step": ref.sample_desc()},
+        "ratio": total_b / total_c,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                         "sample": ref.sample_desc()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# this framework
+# --------------------------------------------------------------------------- #
+
+def run_native(args):
+    import torch
+    import lz77_b200
+    from lz77_b200 import api, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this codec has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    lz77_b200.init(local_rank)
+    sb, la, n = WORKLOAD["sb"], WORKLOAD["la"], args.bytes or WORKLOAD["n"]
+    T = lz77_b200.token_bits(sb, la)
+
+    # every rank owns its own shard of whole blocks (weak scaling): no data-path
+    # collective, the ranks only meet at the timing barrier
+    src = synth.make(WORKLOAD["kind"], n, seed=WORKLOAD["seed"] + rank, device=dev)
+    cap = (api.encode_bound(n, sb, la) + 15) & ~15
+    stream_buf = torch.empty(cap, dtype=torch.uint8, device=dev)
+    out_buf = torch.empty((n + 15) & ~15, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    stream_t = torch.cuda.current_stream(dev)
+    api.set_stream(stream_t.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        s, k = api.encode_tensor(src, la=la, sb=sb, out=stream_buf)
+        t_enc = api.last_timing()
+        back = api.decode_tensor(s, out=out_buf)
+        t_dec = api.last_timing()
+        return s, k, back, t_enc, t_dec
+
+    for _ in range(args.warmup):
+        s, k, back, _, _ = device_step()
+    c_bytes = s.numel()
+    assert torch.equal(back, src), "roundtrip mismatch"
+
+    # ---- timed region: device-resident ------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    per = {"enc_search_ms": [], "enc_scan_ms": [], "enc_pack_ms": [], "dec_scan_ms": [],
+           "dec_copy_ms": []}
+    launches = 0
+    barrier()
+    ev[0].record(stream_t)
+    for i in range(args.steps):
+        s, k = api.encode_tensor(src, la=la, sb=sb, out=stream_buf)
+        t_enc = api.last_timing()
+        ev[2 * i + 1].record(stream_t)
+        back = api.decode_tensor(s, out=out_buf)
+        t_dec = api.last_timing()
+        ev[2 * i + 2].record(stream_t)
+        launches += t_enc["launches"] + t_dec["launches"]
+        for key in ("enc_search_ms", "enc_scan_ms", "enc_pack_ms"):
+            per[key].append(t_enc[key])
+        for key in ("dec_scan_ms", "dec_copy_ms"):
+            per[key].append(t_dec[key])
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    enc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
+    dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    clocks = sampler.stop()
+
+    # ---- timed region: end to end through the host entry points -----------
+    h_in = api.PinnedBuffer(n)
+    h_stream = api.PinnedBuffer(cap)
+    h_out = api.PinnedBuffer(n + 16)
+    h_in.array[:] = src.cpu().numpy()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(args.warmup, 2)):
+        c = api.encode_into(h_in.ptr, n, h_stream.ptr, cap, la=la, sb=sb)
+        m = api.decode_into(h_stream.ptr, c, h_out.ptr, n)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream_t)
+    for _ in range(e2e_steps):
+        c = api.encode_into(h_in.ptr, n, h_stream.ptr, cap, la=la, sb=sb)
+        m = api.decode_into(h_stream.ptr, c, h_out.ptr, n)
+    e1.record(stream_t)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    assert m == n and bytes(h_out.array[:4096]) == bytes(h_in.array[:4096])
+    assert (h_out.array[:n] == h_in.array[:n]).all(), "e2e roundtrip mismatch"
+
+    # ---- max over ranks ----------------------------------------------------
+    times = torch.tensor([total_ms, enc_ms, dec_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms, e2e_ms = times.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        med = {k_: statistics.median(v) for k_, v in per.items()}
+        step_ms = total_ms / args.steps
+        alg_bytes = n + c_bytes     # N + C per direction, per launch
+        search_gbs = alg_bytes / (med["enc_search_ms"] * 1e-3) / 1e9
+        copy_gbs = alg_bytes / (med["dec_copy_ms"] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * n / (step_ms * 1e-3) / 1e9, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"], "bytes_per_gpu": n, "sb": sb, "la": la,
+                       "token_bits": T, "block_bytes": lz77_b200.block_size(sb),
+                       "segment_bytes": lz77_b200.segment_size(),
+                       "sharding": f"{world} rank(s), whole blocks per rank, no collective",
+                       "l2": "inputs (256 MiB) larger than L2 (126 MB); no flush needed"},
+            "encode_gbs": world * n / (enc_ms * 1e-3) / 1e9,
+            "decode_gbs": world * n / (dec_ms * 1e-3) / 1e9,
+            "ratio": n / c_bytes, "tokens": k,
+            "kernel_ms": med,
+            "e2e": {"value": world * n / (e2e_ms / e2e_steps * 1e-3) / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": n + c_bytes, "d2h_bytes_per_step": c_bytes + n,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "lz77_parse_kernel (longest-match search + greedy parse)",
+                         "bound": "hbm", "achieved": search_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": search_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes},
+            "roofline_decode": {"kernel": "lz77_decode_tile_kernel (match copy)",
+                                "bound": "hbm", "achieved": copy_gbs, "peak": peak,
+                                "unit": "GB/s", "frac": copy_gbs / peak, "traffic": None,
+                                "algorithmic_bytes": alg_bytes},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                ref = CpuReference(slice_bytes=args.ref_slice_mib << 20)
+                dt, b, c_ref = ref.step()
+                line["cpu_baseline"] = {"value": b / dt / 1e9, "unit": UNIT, "cores": ref.cores,
+                                        "kind": ref.kind, "sample": ref.sample_desc(),
+                                        "ratio": b / c_ref}
+            except Exception as exc:  # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                        "sample": f"failed: {exc}"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--bytes", type=int, default=0, help="override the per-GPU input size")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-slice-mib", type=int, default=8,
+                    help="per-core slice the CPU reference encodes+decodes per sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

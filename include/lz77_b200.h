@@ -79,6 +79,11 @@ void lz77_gpu_shutdown(void);
 const char *lz77_gpu_strerror(int rc);
 const char *lz77_gpu_last_error(void);
 
+/* Run every later call on the caller's CUDA stream (a cudaStream_t passed as
+ * void*) instead of the library's own; NULL restores the library's stream.
+ * Calls stay synchronous: the stream is drained before they return. */
+int  lz77_gpu_set_stream(void *cuda_stream);
+
 /* pinned host memory for fast host<->device copies (optional) */
 void *lz77_gpu_host_alloc(long n);
 void  lz77_gpu_host_free(void *p);

@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     block_size,
     decode,
     decode_size,
+    decode_size_tensor,
     decode_tensor,
     encode,
     encode_bound,
@@ -21,6 +22,8 @@ from .api import (  # noqa: F401
     init,
     last_timing,
     load_library,
+    set_stream,
+    set_timing,
     segment_size,
     shutdown,
     token_bits,

@@ -27,7 +27,7 @@ EXPORTS = (
     "lz77_gpu_strerror", "lz77_gpu_last_error", "lz77_gpu_host_alloc", "lz77_gpu_host_free",
     "lz77_gpu_encode", "lz77_gpu_decode_size", "lz77_gpu_decode", "lz77_gpu_encode_device",
     "lz77_gpu_decode_size_device", "lz77_gpu_decode_device", "lz77_gpu_last_timing",
-    "lz77_gpu_set_timing",
+    "lz77_gpu_set_timing", "lz77_gpu_set_stream",
 )
 
 
@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
         "lz77_gpu_decode_device": (ip, [vp, lp, vp, lp, plong]),
         "lz77_gpu_last_timing": (ip, [C.POINTER(Timing)]),
         "lz77_gpu_set_timing": (None, [ip]),
+        "lz77_gpu_set_stream": (ip, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -155,6 +156,12 @@ def last_timing() -> dict:
     t = Timing()
     _check(load_library().lz77_gpu_last_timing(C.byref(t)))
     return t.as_dict()
+
+
+def set_stream(cuda_stream: int | None) -> None:
+    """Run later calls on this CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``);
+    None restores the library's own stream."""
+    _check(load_library().lz77_gpu_set_stream(cuda_stream or None))
 
 
 def set_timing(enabled: bool) -> None:

@@ -19,7 +19,8 @@ namespace {
 struct Context {
     bool ready = false;
     int device = -1;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream every call uses
+    cudaStream_t own_stream = nullptr;  // created by init; used unless the caller sets one
     void *scratch = nullptr;
     size_t scratch_cap = 0;
     void *stage_in = nullptr;   // device staging for the host entry points
@@ -140,7 +141,7 @@ void lz77_gpu_shutdown(void)
     if (g.stage_in) cudaFree(g.stage_in);
     if (g.stage_out) cudaFree(g.stage_out);
     if (g.pinned) cudaFreeHost(g.pinned);
-    cudaStreamDestroy(g.stream);
+    cudaStreamDestroy(g.own_stream);
     g = Context();
 }
 
@@ -155,7 +156,8 @@ int lz77_gpu_init(int device)
     }
     if (device < 0 || device >= n) return LZ77_E_ARG;
     CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
     for (auto &e : g.ev) CK(cudaEventCreate(&e));
     CK(cudaMallocHost((void **)&g.pinned, 256));
     g.device = device;
@@ -197,6 +199,14 @@ void lz77_gpu_host_free(void *p)
 }
 
 void lz77_gpu_set_timing(int enabled) { g.timing = enabled != 0; }
+
+int lz77_gpu_set_stream(void *cuda_stream)
+{
+    if (!g.ready) return LZ77_E_NODEVICE;
+    cudaStreamSynchronize(g.stream);
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own_stream;
+    return LZ77_OK;
+}
 
 int lz77_gpu_last_timing(struct lz77_timing *t)
 {
