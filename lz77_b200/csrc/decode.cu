@@ -198,6 +198,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_
     return r;
 }
 
+constexpr uint32_t kGroupDone = 0x80000000u;  // top bit of gpos[g]: group g is final
+constexpr uint32_t kGroupPos = 0x7fffffffu;
+
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
@@ -210,10 +213,14 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
     constexpr int kWarps = kThreads / 32;
     const int tile_bytes = 1 << tile_shift;
     uint8_t *tile = smem;
-    uint32_t *gpos = reinterpret_cast<uint32_t *>(smem + tile_bytes);  // group start offsets
+    // gpos[g]: output offset of group g (32 tokens) relative to the tile's first
+    // token, top bit = "every byte of this group is final"
+    volatile uint32_t *gpos = reinterpret_cast<volatile uint32_t *>(smem + tile_bytes);
+    // gmap[c]: the group that contains tile byte 64*c
+    uint16_t *gmap = reinterpret_cast<uint16_t *>(smem + tile_bytes + ((tile_bytes >> 5) + 8) * 4);
 
     __shared__ long long s_tile;
-    __shared__ volatile int s_frontier;
+    __shared__ int s_next_group;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
 
@@ -223,7 +230,10 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
     const int lit_shift = P.ob + P.lb;
 
     while (true) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&tickets[1], 1u);  // tiles start in order
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(&tickets[1], 1u);  // tiles start in order
+            s_next_group = 0;
+        }
         __syncthreads();
         const long long j = s_tile;
         if (j >= n_tiles) break;
@@ -265,12 +275,23 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                     run += v;
                 }
             }
-            if (threadIdx.x == 0) s_frontier = p0_rel;
+            if (threadIdx.x == 0) gpos[n_groups] = s_total;
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < n_groups; g += kThreads) {
+            const int gs = p0_rel + (int)gpos[g], ge = p0_rel + (int)gpos[g + 1];
+            const int c_hi = min((ge + 63) >> 6, (tile_len + 63) >> 6);
+            for (int c = max((gs + 63) >> 6, 0); c < c_hi; c++) gmap[c] = (uint16_t)g;
         }
         __syncthreads();
 
-        // ---- phase 2: groups in order, one lane per token ------------------
-        for (int g = warp; g < n_groups; g += kWarps) {
+        // ---- phase 2: one lane per token, groups handed out in order -------
+        while (true) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&s_next_group, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= n_groups) break;
+
             const long long k = k0 + g * 32 + lane;
             const bool valid = k < k_end;
             uint32_t tok = 0;
@@ -285,9 +306,8 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                 int t = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += t;
             }
-            const int gs_rel = p0_rel + (int)gpos[g];
-            const int ge_rel = gs_rel + __shfl_sync(0xffffffffu, inc, 31);
-            const int pos_rel = gs_rel + inc - l1;
+            const uint32_t gpos_g = gpos[g];
+            const int pos_rel = p0_rel + (int)(gpos_g & kGroupPos) + inc - l1;
 
             if (valid) {  // literal, lz77.c:189-194
                 const int d = pos_rel + len;
@@ -298,23 +318,39 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                 info->error = 1;  // source before the start of the output
                 pending = false;
             }
-            const int s_rel = pos_rel - off;           // first source byte
-            const int e_rel = s_rel + min(len, off);   // one past the last distinct source byte
+            // every source byte lies in [s_rel, e_rel), strictly before the token
+            // (a self-overlapping match repeats its first `off` bytes)
+            const int s_rel = pos_rel - off;
+            const int e_rel = s_rel + min(len, off);
+            bool ext = pending && s_rel < 0;  // reaches into earlier tiles
             unsigned int ta = 0, tb = 0;
-            bool ext = pending && s_rel < 0;           // reaches into earlier tiles
             if (ext) {
                 ta = (unsigned int)((tile_lo + s_rel) >> tile_shift);
                 tb = (unsigned int)((tile_lo + min(e_rel, 0) - 1) >> tile_shift);
             }
+            // groups [ga, gb] hold the in-tile source bytes; gb == g: partly in this group
+            int ga = 0, gb = -1;
+            if (pending && e_rel > 0) {
+                const int a0 = max(s_rel, 0);
+                ga = gmap[a0 >> 6];
+                while (p0_rel + (int)(gpos[ga + 1] & kGroupPos) <= a0) ga++;
+                gb = ga;
+                while (p0_rel + (int)(gpos[gb + 1] & kGroupPos) < e_rel) gb++;
+            }
+            const bool own = gb >= g;  // (gb > g cannot happen: sources precede the token)
+            if (own) gb = g - 1;
             __syncwarp();
 
             while (true) {
                 const unsigned um = __ballot_sync(0xffffffffu, pending);
                 if (!um) break;
-                const int F = s_frontier;
+                // bytes of this group below the first unresolved token are final
                 const int pfirst = __shfl_sync(0xffffffffu, pos_rel, __ffs(um) - 1);
-                const int Fl = (F >= gs_rel) ? pfirst : F;  // bytes below Fl are final
-                bool ready = pending && (e_rel <= 0 || e_rel <= Fl);
+                bool ready = pending && (!own || e_rel <= pfirst);
+                if (ready) {
+                    while (ga <= gb && (gpos[ga] & kGroupDone)) ga++;
+                    ready = ga > gb;
+                }
                 if (ready && ext) {
                     ready = ld_acquire_u32(&tile_done[ta]) != 0u &&
                             ld_acquire_u32(&tile_done[tb]) != 0u;
@@ -324,7 +360,8 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                     int r = 0;
                     for (int i = 0; i < len; i++) {
                         const int a = s_rel + r;
-                        const uint8_t c = a >= 0 ? tile[a] : __ldcg(out + (tile_lo + a));
+                        const uint8_t c = a >= 0 ? const_cast<volatile uint8_t *>(tile)[a]
+                                                 : __ldcg(out + (tile_lo + a));
                         const int d = pos_rel + i;
                         if (d >= 0 && d < tile_len) tile[d] = c;
                         if (++r == off) r = 0;
@@ -332,14 +369,11 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                     pending = false;
                 }
                 __syncwarp();
-                if (!__any_sync(0xffffffffu, ready)) __nanosleep(40);
             }
             if (lane == 0) {
-                while (s_frontier != gs_rel) __nanosleep(20);
                 __threadfence_block();
-                s_frontier = ge_rel;
+                gpos[g] = gpos_g | kGroupDone;
             }
-            __syncwarp();
         }
         __syncthreads();
 
@@ -429,7 +463,8 @@ cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
     const long long n_tiles = (n_out + tile_bytes - 1) >> tile_shift;
     const long long n_words = (n_in_bytes + 3) / 4;
     if (n_tiles == 0) return cudaSuccess;
-    const size_t smem = (size_t)tile_bytes + ((size_t)(tile_bytes >> 5) + 8) * 4;
+    const size_t smem = (size_t)tile_bytes + ((size_t)(tile_bytes >> 5) + 8) * 4 +
+                        ((size_t)(tile_bytes >> 6) + 8) * 2;
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
