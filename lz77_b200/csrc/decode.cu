@@ -369,6 +369,8 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                     pending = false;
                 }
                 __syncwarp();
+                // nothing moved: back off so the warps we wait for get the issue slots
+                if (!__any_sync(0xffffffffu, ready)) __nanosleep(100);
             }
             if (lane == 0) {
                 __threadfence_block();

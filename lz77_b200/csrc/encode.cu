@@ -10,8 +10,9 @@
 //
 // The result is the stream oracle/lz77_oracle.c:lz77o_blocked_encode() defines,
 // byte for byte: inside a block the longest match (<= min(LA, bytes left in the
-// segment) - 1) against the last min(window, position in block) bytes, nearest
-// offset among the longest, then a literal.
+// segment) - 1) against the last min(window, position in block) bytes, farthest
+// offset among the longest (keeps the decoder's dependency chains short), then
+// a literal.
 #include "kernels.cuh"
 
 namespace lz77 {
@@ -22,10 +23,10 @@ namespace lz77 {
 //
 // One CTA stages `hist` history bytes + nwarps*kSegBytes input bytes into
 // shared memory with one TMA bulk copy; warp w then parses segment w.  For every
-// token the warp scans the window nearest-first in 512-byte chunks: each lane
+// token the warp scans the window oldest-first in 512-byte chunks: each lane
 // takes one 16-byte group (LDS.128), filters the 16 candidate starts on the
 // first target byte with an exact SWAR zero-byte test, verifies survivors
-// against the target held in registers, and the (length, nearest start) pair is
+// against the target held in registers, and the (length, oldest start) pair is
 // reduced warp-wide with REDUX.  A chunk that yields a maximum-length match
 // ends the scan early.
 
@@ -149,20 +150,20 @@ lz77_parse_kernel(const uint8_t *__restrict__ in, long long n, Params P, int his
             const uint32_t b0x4 = (uint32_t)smem[p0] * 0x01010101u;
             int best_len = 0, best_q = 0;
 
-            for (int base = ((p0 + 15) & ~15) - 512; base + 512 > lo_idx; base -= 512) {
+            for (int base = lo_idx & ~15; base < p0; base += 512) {  // oldest chunk first
                 const int g = base + lane * 16;
-                if (g + 16 > lo_idx && g < p0) {
+                if (g < p0) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(smem + g);
                     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int i = 3; i >= 0; i--) {
+                    for (int i = 0; i < 4; i++) {
                         uint32_t m = zero_bytes(wv[i] ^ b0x4);
                         while (m) {
-                            const int bit = 31 - __clz(m);
+                            const int bit = __ffs(m) - 1;
                             m ^= 1u << bit;
                             const int q = g + 4 * i + (bit >> 3);
                             if (q >= lo_idx && q < p0) {
-                                // farther than anything this lane has seen: must be longer
+                                // nearer than anything this lane has seen: must be longer
                                 const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
                                 if (l > best_len) {
                                     best_len = l;
@@ -174,12 +175,14 @@ lz77_parse_kernel(const uint8_t *__restrict__ in, long long n, Params P, int his
                 }
                 if (__any_sync(0xffffffffu, best_len >= max_len)) break;
             }
+            // longest first, then the oldest start
             key = __reduce_max_sync(0xffffffffu,
-                                    best_len ? ((uint32_t)best_len << 20) | (uint32_t)best_q : 0u);
+                                    best_len ? ((uint32_t)best_len << 20) |
+                                                   (0xfffffu - (uint32_t)best_q) : 0u);
         }
 
         const int len = (int)(key >> 20);
-        const int off = len ? p0 - (int)(key & 0xfffffu) : 0;
+        const int off = len ? p0 - (int)(0xfffffu - (key & 0xfffffu)) : 0;
         const uint32_t lit = smem[p0 + len];
         const uint32_t tok = (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
 

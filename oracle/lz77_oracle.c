@@ -478,17 +478,21 @@ long lz77o_unpack_tokens(const uint8_t *in, long n_in, int *sb, int *la,
 /* block-parallel encoder specification                                     */
 /* ------------------------------------------------------------------------ */
 
-/* Longest match for the lookahead at blk[p] against starts p-1 .. p-reach
- * (nearest first, strictly longer wins => nearest offset among the longest),
- * capped at max_len.  Candidate strings may run into the lookahead, as in
- * tree.c:136 where window[node.off + i] has no upper clamp. */
+/* Longest match for the lookahead at blk[p] against starts p-reach .. p-1,
+ * OLDEST first, strictly longer wins => the farthest offset among the longest
+ * (the reference's BST also tends to answer with the oldest suffix: its root
+ * is the oldest node, see the 1,16,31.. offsets of SURVEY.md Appendix C).  The
+ * choice among equal-length candidates does not change the token count; the
+ * oldest one keeps the decoder's dependency chains short.  Capped at max_len.
+ * Candidate strings may run into the lookahead, as in tree.c:136 where
+ * window[node.off + i] has no upper clamp. */
 static void longest_match(const uint8_t *blk, long p, long reach, int max_len,
                           int *m_off, int *m_len)
 {
     int best = 0, best_off = 0;
     if (max_len > 0) {
         const uint8_t *a = blk + p;
-        for (long d = 1; d <= reach; d++) {
+        for (long d = reach; d >= 1; d--) {
             const uint8_t *b = a - d;
             if (b[best] != a[best] || b[0] != a[0])
                 continue;

@@ -64,7 +64,7 @@ long lz77o_decode(const uint8_t *in, long n_in, uint8_t *out, long out_cap);
  * Specification of the block-parallel encoder the GPU implements: the input
  * is cut into independent blocks of `block` bytes; inside a block each token
  * is the longest match (<= min(la, bytes left in block) - 1) against the last
- * min(sb, 2^bitof(sb) - 1, position in block) bytes, nearest offset winning
+ * min(sb, 2^bitof(sb) - 1, position in block) bytes, farthest offset winning
  * ties, followed by a literal -- i.e. the greedy parse tree.c:118-152 /
  * lz77.c:87-135 produce, restarted at every block.  block <= 0 means one
  * block (the whole input).  n_tokens (may be NULL) receives the token count.
