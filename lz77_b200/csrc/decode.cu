@@ -198,8 +198,33 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_
     return r;
 }
 
-constexpr uint32_t kGroupDone = 0x80000000u;  // top bit of gpos[g]: group g is final
-constexpr uint32_t kGroupPos = 0x7fffffffu;
+// ready bitmap: bit i of the tile is set once byte i holds its final value
+__device__ __forceinline__ void ready_mark(uint32_t *bits, int a, int b)  // [a, b), a < b
+{
+    const int w0 = a >> 5, w1 = (b - 1) >> 5;
+    const uint32_t first = 0xffffffffu << (a & 31);
+    const uint32_t last = 0xffffffffu >> (31 - ((b - 1) & 31));
+    if (w0 == w1) {
+        atomicOr(bits + w0, first & last);
+    } else {
+        atomicOr(bits + w0, first);
+        for (int w = w0 + 1; w < w1; w++) atomicOr(bits + w, 0xffffffffu);
+        atomicOr(bits + w1, last);
+    }
+}
+
+// advances a over the bytes of [a, b) that are ready; true when all of them are
+__device__ __forceinline__ bool ready_test(const volatile uint32_t *bits, int &a, int b)
+{
+    while (a < b) {
+        const int w = a >> 5;
+        const int end = min(b, (w + 1) << 5);
+        const uint32_t mask = (0xffffffffu << (a & 31)) & (0xffffffffu >> (31 - ((end - 1) & 31)));
+        if ((bits[w] & mask) != mask) return false;
+        a = end;
+    }
+    return true;
+}
 
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
@@ -213,11 +238,11 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
     constexpr int kWarps = kThreads / 32;
     const int tile_bytes = 1 << tile_shift;
     uint8_t *tile = smem;
-    // gpos[g]: output offset of group g (32 tokens) relative to the tile's first
-    // token, top bit = "every byte of this group is final"
-    volatile uint32_t *gpos = reinterpret_cast<volatile uint32_t *>(smem + tile_bytes);
-    // gmap[c]: the group that contains tile byte 64*c
-    uint16_t *gmap = reinterpret_cast<uint16_t *>(smem + tile_bytes + ((tile_bytes >> 5) + 8) * 4);
+    // gpos[g]: output offset of group g (32 tokens) relative to the tile's first token
+    uint32_t *gpos = reinterpret_cast<uint32_t *>(smem + tile_bytes);
+    // one bit per tile byte: the byte holds its final value
+    uint32_t *ready_bits =
+        reinterpret_cast<uint32_t *>(smem + tile_bytes + ((tile_bytes >> 5) + 8) * 4);
 
     __shared__ long long s_tile;
     __shared__ int s_next_group;
@@ -250,6 +275,7 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
         const int n_groups = (n_tok + 31) >> 5;
 
         // ---- phase 1: output offset of every group of 32 tokens -----------
+        for (int i = threadIdx.x; i < (tile_bytes >> 5); i += kThreads) ready_bits[i] = 0u;
         for (int g = warp; g < n_groups; g += kWarps) {
             const long long k = k0 + g * 32 + lane;
             uint32_t l1 = 0;
@@ -275,13 +301,6 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                     run += v;
                 }
             }
-            if (threadIdx.x == 0) gpos[n_groups] = s_total;
-        }
-        __syncthreads();
-        for (int g = threadIdx.x; g < n_groups; g += kThreads) {
-            const int gs = p0_rel + (int)gpos[g], ge = p0_rel + (int)gpos[g + 1];
-            const int c_hi = min((ge + 63) >> 6, (tile_len + 63) >> 6);
-            for (int c = max((gs + 63) >> 6, 0); c < c_hi; c++) gmap[c] = (uint16_t)g;
         }
         __syncthreads();
 
@@ -306,8 +325,9 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                 int t = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += t;
             }
-            const uint32_t gpos_g = gpos[g];
-            const int pos_rel = p0_rel + (int)(gpos_g & kGroupPos) + inc - l1;
+            const int pos_rel = p0_rel + (int)gpos[g] + inc - l1;
+            // the part of this token that lies in the tile
+            const int d_lo = max(pos_rel, 0), d_hi = min(pos_rel + l1, tile_len);
 
             if (valid) {  // literal, lz77.c:189-194
                 const int d = pos_rel + len;
@@ -322,35 +342,22 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
             // (a self-overlapping match repeats its first `off` bytes)
             const int s_rel = pos_rel - off;
             const int e_rel = s_rel + min(len, off);
+            int chk = max(s_rel, 0);          // in-tile source bytes below chk are known ready
             bool ext = pending && s_rel < 0;  // reaches into earlier tiles
             unsigned int ta = 0, tb = 0;
             if (ext) {
                 ta = (unsigned int)((tile_lo + s_rel) >> tile_shift);
                 tb = (unsigned int)((tile_lo + min(e_rel, 0) - 1) >> tile_shift);
             }
-            // groups [ga, gb] hold the in-tile source bytes; gb == g: partly in this group
-            int ga = 0, gb = -1;
-            if (pending && e_rel > 0) {
-                const int a0 = max(s_rel, 0);
-                ga = gmap[a0 >> 6];
-                while (p0_rel + (int)(gpos[ga + 1] & kGroupPos) <= a0) ga++;
-                gb = ga;
-                while (p0_rel + (int)(gpos[gb + 1] & kGroupPos) < e_rel) gb++;
-            }
-            const bool own = gb >= g;  // (gb > g cannot happen: sources precede the token)
-            if (own) gb = g - 1;
+            __threadfence_block();
+            if (valid && !pending && d_lo < d_hi) ready_mark(ready_bits, d_lo, d_hi);
             __syncwarp();
 
+            int spins = 0;
             while (true) {
                 const unsigned um = __ballot_sync(0xffffffffu, pending);
                 if (!um) break;
-                // bytes of this group below the first unresolved token are final
-                const int pfirst = __shfl_sync(0xffffffffu, pos_rel, __ffs(um) - 1);
-                bool ready = pending && (!own || e_rel <= pfirst);
-                if (ready) {
-                    while (ga <= gb && (gpos[ga] & kGroupDone)) ga++;
-                    ready = ga > gb;
-                }
+                bool ready = pending && ready_test(ready_bits, chk, e_rel);
                 if (ready && ext) {
                     ready = ld_acquire_u32(&tile_done[ta]) != 0u &&
                             ld_acquire_u32(&tile_done[tb]) != 0u;
@@ -366,15 +373,13 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                         if (d >= 0 && d < tile_len) tile[d] = c;
                         if (++r == off) r = 0;
                     }
+                    __threadfence_block();
+                    if (d_lo < d_hi) ready_mark(ready_bits, d_lo, d_hi);
                     pending = false;
                 }
                 __syncwarp();
                 // nothing moved: back off so the warps we wait for get the issue slots
-                if (!__any_sync(0xffffffffu, ready)) __nanosleep(100);
-            }
-            if (lane == 0) {
-                __threadfence_block();
-                gpos[g] = gpos_g | kGroupDone;
+                if (!__any_sync(0xffffffffu, ready) && ++spins > 4) __nanosleep(64);
             }
         }
         __syncthreads();
@@ -466,19 +471,19 @@ cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
     const long long n_words = (n_in_bytes + 3) / 4;
     if (n_tiles == 0) return cudaSuccess;
     const size_t smem = (size_t)tile_bytes + ((size_t)(tile_bytes >> 5) + 8) * 4 +
-                        ((size_t)(tile_bytes >> 6) + 8) * 2;
+                        (size_t)(tile_bytes >> 3);  // tile + group offsets + ready bitmap
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (tile_bytes <= 65536) {
-        auto kern = lz77_decode_tile_kernel<512, 3>;
+        auto kern = lz77_decode_tile_kernel<768, 2>;
         cudaError_t rc =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
-        long long grid = (long long)sms * 3;
+        long long grid = (long long)sms * 2;
         if (grid > n_tiles) grid = n_tiles;
-        kern<<<(unsigned)grid, 512, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
+        kern<<<(unsigned)grid, 768, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
                                                  s.tile_tok, s.tile_pos, n_tiles, n_out, d_out,
                                                  s.tile_done, s.tickets, s.info);
     } else {
