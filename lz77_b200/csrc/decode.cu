@@ -353,33 +353,63 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
             if (valid && !pending && d_lo < d_hi) ready_mark(ready_bits, d_lo, d_hi);
             __syncwarp();
 
+            // token and sources entirely inside the tile: the common, cheap copy
+            const bool fast = pos_rel >= 0 && s_rel >= 0 && pos_rel + len <= tile_len;
+            bool ready = false;  // sources final, copy still to do
+            unsigned prev_rm = 0;
             int spins = 0;
             while (true) {
                 const unsigned um = __ballot_sync(0xffffffffu, pending);
                 if (!um) break;
-                bool ready = pending && ready_test(ready_bits, chk, e_rel);
-                if (ready && ext) {
-                    ready = ld_acquire_u32(&tile_done[ta]) != 0u &&
-                            ld_acquire_u32(&tile_done[tb]) != 0u;
-                    if (ready) ext = false;
-                }
-                if (ready) {  // ascending byte copy, lz77.c:178-188
-                    int r = 0;
-                    for (int i = 0; i < len; i++) {
-                        const int a = s_rel + r;
-                        const uint8_t c = a >= 0 ? const_cast<volatile uint8_t *>(tile)[a]
-                                                 : __ldcg(out + (tile_lo + a));
-                        const int d = pos_rel + i;
-                        if (d >= 0 && d < tile_len) tile[d] = c;
-                        if (++r == off) r = 0;
+                if (pending && !ready) {  // cheap poll of the ready bitmap
+                    ready = ready_test(ready_bits, chk, e_rel);
+                    if (ready && ext) {
+                        ready = ld_acquire_u32(&tile_done[ta]) != 0u &&
+                                ld_acquire_u32(&tile_done[tb]) != 0u;
+                        if (ready) ext = false;
                     }
-                    __threadfence_block();
-                    if (d_lo < d_hi) ready_mark(ready_bits, d_lo, d_hi);
-                    pending = false;
                 }
-                __syncwarp();
-                // nothing moved: back off so the warps we wait for get the issue slots
-                if (!__any_sync(0xffffffffu, ready) && ++spins > 4) __nanosleep(64);
+                const unsigned rm = __ballot_sync(0xffffffffu, ready);
+                // copy in as few divergent passes as possible: when every pending
+                // lane is ready, or when the ready set stopped growing
+                const bool go = rm != 0u && (rm == um || rm == prev_rm);
+                prev_rm = rm;
+                if (go) {
+                    if (ready) {  // ascending byte copy, lz77.c:178-188
+                        if (fast) {
+                            const volatile uint8_t *src = tile + s_rel;
+                            uint8_t *dst = tile + pos_rel;
+                            if (off >= len) {
+                                for (int i = 0; i < len; i++) dst[i] = src[i];
+                            } else {
+                                int r = 0;
+                                for (int i = 0; i < len; i++) {
+                                    dst[i] = src[r];
+                                    if (++r == off) r = 0;
+                                }
+                            }
+                        } else {
+                            int r = 0;
+                            for (int i = 0; i < len; i++) {
+                                const int a = s_rel + r;
+                                const uint8_t c = a >= 0 ? const_cast<volatile uint8_t *>(tile)[a]
+                                                         : __ldcg(out + (tile_lo + a));
+                                const int d = pos_rel + i;
+                                if (d >= 0 && d < tile_len) tile[d] = c;
+                                if (++r == off) r = 0;
+                            }
+                        }
+                        __threadfence_block();
+                        if (d_lo < d_hi) ready_mark(ready_bits, d_lo, d_hi);
+                        pending = false;
+                        ready = false;
+                    }
+                    __syncwarp();
+                    prev_rm = 0;
+                    spins = 0;
+                } else if (rm == 0u && ++spins > 2) {
+                    __nanosleep(40);  // leave the issue slots to the warps we wait for
+                }
             }
         }
         __syncthreads();
