@@ -123,4 +123,35 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// CTA-wide exclusive prefix sum of one value per thread (all threads must call)
+template <int kThreads>
+__device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_t *s_warp,
+                                                             uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = lane < kThreads / 32 ? s_warp[lane] : 0u;
+        uint32_t sinc = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, sinc, d);
+            if (lane >= d) sinc += t;
+        }
+        s_warp[lane] = sinc - s;
+        if (lane == 31) *total = sinc;
+    }
+    __syncthreads();
+    const uint32_t r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
 }  // namespace lz77

@@ -168,36 +168,6 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
 // pass 2: tile decode
 // ---------------------------------------------------------------------------
 
-template <int kThreads>
-__device__ __forceinline__ uint32_t block_exclusive_scan_u32(uint32_t v, uint32_t *s_warp,
-                                                             uint32_t *total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t s = lane < kThreads / 32 ? s_warp[lane] : 0u;
-        uint32_t sinc = s;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, sinc, d);
-            if (lane >= d) sinc += t;
-        }
-        s_warp[lane] = sinc - s;
-        if (lane == 31) *total = sinc;
-    }
-    __syncthreads();
-    const uint32_t r = s_warp[warp] + inc - v;
-    __syncthreads();
-    return r;
-}
-
 // ready bitmap: bit i of the tile is set once byte i holds its final value
 __device__ __forceinline__ void ready_mark(uint32_t *bits, int a, int b)  // [a, b), a < b
 {

@@ -14,6 +14,7 @@
 // offset among the longest (keeps the decoder's dependency chains short), then
 // a literal.
 #include "kernels.cuh"
+#include "match.cuh"
 
 namespace lz77 {
 
@@ -29,54 +30,6 @@ namespace lz77 {
 // against the target held in registers, and the (length, oldest start) pair is
 // reduced warp-wide with REDUX.  A chunk that yields a maximum-length match
 // ends the scan early.
-
-template <bool kSmallLA>
-__device__ __forceinline__ int match_len(const uint8_t *smem, int q, int p0,
-                                         const uint32_t (&tgt)[4], int max_len)
-{
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (q & ~3));
-    const int sh = (q & 3) * 8;
-    if (kSmallLA) {  // LA <= 16: target in registers, at most 4 words
-        uint32_t a0 = w[0], a1 = w[1];
-        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
-        int l;
-        if (x) {
-            l = (__ffs(x) - 1) >> 3;
-        } else {
-            uint32_t a2 = w[2];
-            x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
-            if (x) {
-                l = 4 + ((__ffs(x) - 1) >> 3);
-            } else {
-                uint32_t a3 = w[3];
-                x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
-                if (x) {
-                    l = 8 + ((__ffs(x) - 1) >> 3);
-                } else {
-                    uint32_t a4 = w[4];
-                    x = __funnelshift_r(a3, a4, sh) ^ tgt[3];
-                    l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
-                }
-            }
-        }
-        return min(l, max_len);
-    } else {
-        int l = 0;
-        uint32_t a = w[0];
-        int wi = 1;
-        while (l < max_len) {
-            uint32_t b = w[wi++];
-            uint32_t x = __funnelshift_r(a, b, sh) ^ lds_u32_unaligned(smem, p0 + l);
-            if (x) {
-                l += (__ffs(x) - 1) >> 3;
-                break;
-            }
-            l += 4;
-            a = b;
-        }
-        return min(l, max_len);
-    }
-}
 
 template <bool kSmallLA>
 __global__ void __launch_bounds__(1024, 1)
@@ -426,7 +379,11 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, 
     const bool small_la = P.la <= 16;
 
     if (ev) cudaEventRecord(ev->e[0], st);
-    if (n_tiles > 0) {
+    if (n_tiles > 0 && P.window <= 8191) {
+        // small windows: bucketed search (search_bucket.cu)
+        cudaError_t rc = launch_parse_bucket(d_in, n_in, P, tok_tmp, seg_ntok, st);
+        if (rc != cudaSuccess) return rc;
+    } else if (n_tiles > 0) {
         auto kern = small_la ? lz77_parse_kernel<true> : lz77_parse_kernel<false>;
         cudaError_t rc =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

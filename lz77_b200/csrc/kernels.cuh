@@ -18,6 +18,10 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, 
                           uint32_t *d_out_words, unsigned long long **d_total_tokens,
                           cudaStream_t st, StageEvents *ev);
 
+// bucketed longest-match search + greedy parse (search_bucket.cu)
+cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
+                                uint32_t *tok_tmp, uint32_t *seg_ntok, cudaStream_t st);
+
 // ---- decoder (decode.cu) ---------------------------------------------------
 struct DecodeInfo {            // lives in device scratch, copied back by the C ABI
     unsigned long long n_out;  // decoded size

@@ -1,0 +1,59 @@
+// match.cuh -- common-prefix length of a window candidate and the lookahead,
+// the byte loop of the reference's find() (tree.c:136) done a word at a time.
+#pragma once
+
+#include "common.cuh"
+
+namespace lz77 {
+
+// Length of the common prefix of smem[q..] and smem[p0..], capped at max_len.
+// kSmallLA (LA <= 16): the lookahead is held in registers as tgt[0..3].
+template <bool kSmallLA>
+__device__ __forceinline__ int match_len(const uint8_t *smem, int q, int p0,
+                                         const uint32_t (&tgt)[4], int max_len)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (q & ~3));
+    const int sh = (q & 3) * 8;
+    if (kSmallLA) {
+        uint32_t a0 = w[0], a1 = w[1];
+        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+        int l;
+        if (x) {
+            l = (__ffs(x) - 1) >> 3;
+        } else {
+            uint32_t a2 = w[2];
+            x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+            if (x) {
+                l = 4 + ((__ffs(x) - 1) >> 3);
+            } else {
+                uint32_t a3 = w[3];
+                x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+                if (x) {
+                    l = 8 + ((__ffs(x) - 1) >> 3);
+                } else {
+                    uint32_t a4 = w[4];
+                    x = __funnelshift_r(a3, a4, sh) ^ tgt[3];
+                    l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
+                }
+            }
+        }
+        return min(l, max_len);
+    } else {
+        int l = 0;
+        uint32_t a = w[0];
+        int wi = 1;
+        while (l < max_len) {
+            uint32_t b = w[wi++];
+            uint32_t x = __funnelshift_r(a, b, sh) ^ lds_u32_unaligned(smem, p0 + l);
+            if (x) {
+                l += (__ffs(x) - 1) >> 3;
+                break;
+            }
+            l += 4;
+            a = b;
+        }
+        return min(l, max_len);
+    }
+}
+
+}  // namespace lz77

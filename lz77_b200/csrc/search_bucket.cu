@@ -1,0 +1,305 @@
+// search_bucket.cu -- longest-match search over position buckets (sm_100a).
+//
+// Second-generation replacement of the reference's BST match finder
+// (tree.c:62-260).  Same result as the exhaustive window scan in encode.cu --
+// the longest match, farthest offset among the longest -- at a fraction of the
+// instructions: instead of filtering every window byte per token, each CTA
+// first groups the positions of its staged tile by a key of their first two
+// bytes, then a token only verifies the positions that share its key.
+//
+//   build (per tile, all warps)
+//     key(q) = x[q] << 3 | x[q+1] & 7                     (2048 buckets)
+//     stable counting sort of the tile's positions by key: per-warp histogram
+//     of a contiguous chunk (packed 16-bit counters, shared-memory atomics),
+//     column scan across warps + bucket scan, then an in-order scatter whose
+//     intra-row ranks come from MATCH.ANY -- so every bucket lists its
+//     positions in ascending order.
+//   search (per token, one warp)
+//     bucket of the lookahead's key -> warp-ary lower bound of the window start
+//     -> 32 candidates per round, oldest first, verified against the target
+//     held in registers -> (length, oldest start) reduced with REDUX; stops at
+//     the first maximum-length match.
+//     A match of length 1 can sit in any of the 8 buckets that share the first
+//     byte; when nothing longer exists, 8 lanes binary-search those buckets for
+//     the oldest in-window position.
+#include "kernels.cuh"
+#include "match.cuh"
+
+namespace lz77 {
+
+constexpr int kBuckets = 2048;
+
+__device__ __forceinline__ int bucket_key(const uint8_t *smem, int i)
+{
+    return ((int)smem[i] << 3) | ((int)smem[i + 1] & 7);
+}
+
+// first index in [0, n) of the ascending list e[] whose value is >= lo (n if none);
+// warp-uniform, 32 probes per step
+template <typename PosT>
+__device__ __forceinline__ int warp_lower_bound(const PosT *e, int n, int lo, int lane)
+{
+    int base = 0, cnt = n;
+    while (cnt > 32) {
+        const int step = (cnt + 31) >> 5;
+        const int idx = base + lane * step;
+        const bool ge = idx < base + cnt ? (int)e[idx] >= lo : true;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        const int first = m ? __ffs(m) - 1 : 32;
+        if (first == 0) return base;
+        // the answer lies in (probe[first-1], probe[first]]
+        const int nb = base + (first - 1) * step + 1;
+        const int ne = min(base + cnt, base + first * step + 1);
+        base = nb;
+        cnt = ne - nb;
+    }
+    const int idx = base + lane;
+    const bool ge = idx < base + cnt ? (int)e[idx] >= lo : true;
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    return base + (m ? __ffs(m) - 1 : 32);  // lanes beyond cnt report true, so <= base + cnt
+}
+
+template <bool kSmallLA, int kWarps, typename PosT>
+__global__ void __launch_bounds__(kWarps * 32)
+lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
+                         long long n_tiles, uint32_t *__restrict__ tok_tmp,
+                         uint32_t *__restrict__ seg_ntok, PosT *sorted_global,
+                         long long sorted_stride)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+
+    constexpr int kThreads = kWarps * 32;
+    constexpr int kCntWords = kBuckets * (kWarps / 2);  // two 16-bit counters per word
+    const int tile_bytes = kWarps * kSegBytes;
+    const int data_cap = hist_cap + tile_bytes + 64;
+    PosT *bstart = reinterpret_cast<PosT *>(smem + ((data_cap + 15) & ~15));
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bstart) +
+                                                 (((kBuckets + 1) * sizeof(PosT) + 15) & ~15));
+    PosT *sorted = sorted_global ? sorted_global + (long long)blockIdx.x * sorted_stride
+                                 : reinterpret_cast<PosT *>(cnt + kCntWords);
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int cnt_col = warp >> 1, cnt_sh = (warp & 1) * 16;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t phase = 0;
+    for (long long tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x, phase ^= 1u) {
+        const long long tile_lo = tile_i * tile_bytes;
+        const long long blk_lo = (tile_lo >> P.block_shift) << P.block_shift;
+
+        // ---- stage history + tile with one TMA bulk copy -------------------
+        long long hist = tile_lo - blk_lo;
+        if (hist > P.window) hist = P.window;
+        const int hist_al = (int)((hist + 15) & ~15LL);
+        const long long src_lo = tile_lo - hist_al;
+        long long src_hi = tile_lo + tile_bytes;
+        if (src_hi > n) src_hi = n;
+        const int bytes = (int)(src_hi - src_lo);
+        const int bulk = bytes & ~15;
+        const int dst0 = hist_cap - hist_al;  // smem index of global byte src_lo
+
+        if (threadIdx.x == 0 && bulk > 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&mbar, (uint32_t)bulk);
+            tma_load_1d(smem + dst0, in + src_lo, (uint32_t)bulk, &mbar);
+        }
+        for (int i = bulk + threadIdx.x; i < bytes + 64; i += kThreads)
+            smem[dst0 + i] = (i < bytes) ? in[src_lo + i] : (uint8_t)0;
+        for (int i = threadIdx.x; i < kCntWords; i += kThreads) cnt[i] = 0u;
+        if (bulk > 0) mbar_wait(&mbar, phase);
+        __syncthreads();
+
+        // ---- build: stable counting sort of the positions by key -----------
+        const int rows = (bytes + kThreads - 1) / kThreads;  // rows of 32 positions per warp
+        const int cbase = dst0 + warp * rows * 32;
+        const int cend = min(dst0 + bytes, cbase + rows * 32);
+        for (int i = cbase + lane; i < cend; i += 32)
+            atomicAdd(&cnt[bucket_key(smem, i) * (kWarps / 2) + cnt_col], 1u << cnt_sh);
+        __syncthreads();
+        {
+            // thread t owns buckets [t*per, (t+1)*per): exclusive scan across the
+            // warps' counters, then across buckets
+            constexpr int per = kBuckets / kThreads;
+            uint32_t tot[per];
+            uint32_t sum = 0;
+#pragma unroll
+            for (int b = 0; b < per; b++) {
+                uint32_t *c = cnt + (threadIdx.x * per + b) * (kWarps / 2);
+                uint32_t run = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps / 2; w++) {
+                    const uint32_t v = c[w];
+                    const uint32_t lo = v & 0xffffu, hi = v >> 16;
+                    c[w] = run | ((run + lo) << 16);
+                    run += lo + hi;
+                }
+                tot[b] = run;
+                sum += run;
+            }
+            uint32_t base = block_exclusive_scan_u32<kThreads>(sum, s_warp, &s_total);
+#pragma unroll
+            for (int b = 0; b < per; b++) {
+                bstart[threadIdx.x * per + b] = (PosT)base;
+                base += tot[b];
+            }
+            if (threadIdx.x == kThreads - 1) bstart[kBuckets] = (PosT)base;
+        }
+        __syncthreads();
+        for (int r = 0; r < rows; r++) {
+            const int i = cbase + r * 32 + lane;
+            const bool valid = i < cend;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const int key = bucket_key(smem, i);
+                const unsigned peers = __match_any_sync(vmask, key);
+                const int leader = __ffs(peers) - 1;
+                uint32_t old = 0;
+                if (lane == leader)
+                    old = atomicAdd(&cnt[key * (kWarps / 2) + cnt_col],
+                                    (uint32_t)__popc(peers) << cnt_sh);
+                old = __shfl_sync(peers, old, leader);
+                const int slot = (int)bstart[key] + (int)((old >> cnt_sh) & 0xffffu) +
+                                 __popc(peers & lt_mask);
+                sorted[slot] = (PosT)i;
+            }
+        }
+        if (sorted_global) __threadfence_block();
+        __syncthreads();
+
+        // ---- parse this warp's segment -----------------------------------
+        const long long seg_lo = tile_lo + (long long)warp * kSegBytes;
+        const long long sgm = tile_i * kWarps + warp;  // global segment index
+        if (seg_lo < n) {
+            long long seg_hi = seg_lo + kSegBytes;
+            if (seg_hi > n) seg_hi = n;
+            const int seg_end = (int)(seg_hi - src_lo) + dst0;
+            int p0 = (int)(seg_lo - src_lo) + dst0;
+            const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // may be < 0
+            uint32_t *tok_out = tok_tmp + sgm * kSegBytes;
+            const int len_shift = P.ob, lit_shift = P.ob + P.lb;
+            int ntok = 0;
+            uint32_t held = 0;
+
+            while (p0 < seg_end) {
+                const int max_len = min(P.la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
+                const int reach = min(p0 - blk_idx, P.window);    // lz77.c:101-105
+                int len = 0, off = 0;
+
+                if (max_len > 0 && reach > 0) {
+                    const int lo_idx = p0 - reach;
+                    uint32_t tgt[4] = {0, 0, 0, 0};
+                    if (kSmallLA) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) tgt[i] = lds_u32_unaligned(smem, p0 + 4 * i);
+                    }
+                    const int key = bucket_key(smem, p0);
+                    const int bs = (int)bstart[key];
+                    const int bn = (int)bstart[key + 1] - bs;
+                    const PosT *e = sorted + bs;
+                    int best_len = 0, best_q = 0;
+                    // candidates: bucket entries in [lo_idx, p0), oldest first
+                    for (int i = warp_lower_bound(e, bn, lo_idx, lane); i < bn; i += 32) {
+                        const int idx = i + lane;
+                        const int q = idx < bn ? (int)e[idx] : 0x7fffffff;
+                        if (q < p0) {
+                            // nearer than anything this lane has seen: must be longer
+                            const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
+                            if (l > best_len) {
+                                best_len = l;
+                                best_q = q;
+                            }
+                        }
+                        if (__any_sync(0xffffffffu, best_len >= max_len || q >= p0)) break;
+                    }
+                    const uint32_t k = __reduce_max_sync(
+                        0xffffffffu, best_len ? ((uint32_t)best_len << 20) |
+                                                    (0xfffffu - (uint32_t)best_q) : 0u);
+                    len = (int)(k >> 20);
+                    int q_best = (int)(0xfffffu - (k & 0xfffffu));
+                    if (len < 2) {
+                        // length 1: the oldest in-window position with the same first
+                        // byte, in any of the 8 buckets of that byte
+                        int q1 = 0x7fffffff;
+                        if (lane < 8) {
+                            const int kb = (key & ~7) + lane;
+                            const int s1 = (int)bstart[kb];
+                            int lo_i = 0, hi_i = (int)bstart[kb + 1] - s1;
+                            const PosT *e1 = sorted + s1;
+                            const int n1 = hi_i;
+                            while (lo_i < hi_i) {  // lower bound of lo_idx
+                                const int mid = (lo_i + hi_i) >> 1;
+                                if ((int)e1[mid] < lo_idx) lo_i = mid + 1; else hi_i = mid;
+                            }
+                            if (lo_i < n1 && (int)e1[lo_i] < p0) q1 = (int)e1[lo_i];
+                        }
+                        q1 = (int)__reduce_min_sync(0xffffffffu, (unsigned)q1);
+                        if (q1 != 0x7fffffff) {
+                            len = 1;
+                            q_best = q1;
+                        } else {
+                            len = 0;
+                        }
+                    }
+                    off = len ? p0 - q_best : 0;
+                }
+
+                const uint32_t lit = smem[p0 + len];
+                const uint32_t tok =
+                    (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
+                if (lane == (ntok & 31)) held = tok;
+                ntok++;
+                if ((ntok & 31) == 0) tok_out[ntok - 32 + lane] = held;  // coalesced 128 B row
+                p0 += len + 1;
+            }
+            if (lane < (ntok & 31)) tok_out[(ntok & ~31) + lane] = held;
+            if (lane == 0) seg_ntok[sgm] = (uint32_t)ntok;
+        }
+        __syncthreads();  // the next tile overwrites the staged data and the buckets
+    }
+}
+
+// ---------------------------------------------------------------------------
+
+size_t bucket_parse_smem(const Params &P, int nwarps, int hist_cap, bool sorted_in_smem,
+                         size_t pos_bytes)
+{
+    const size_t data_cap = (size_t)hist_cap + (size_t)nwarps * kSegBytes + 64;
+    size_t b = (data_cap + 15) & ~(size_t)15;
+    b += ((kBuckets + 1) * pos_bytes + 15) & ~(size_t)15;
+    b += (size_t)kBuckets * (nwarps / 2) * 4;
+    if (sorted_in_smem) b += data_cap * pos_bytes;
+    (void)P;
+    return b + 16;
+}
+
+cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
+                                uint32_t *tok_tmp, uint32_t *seg_ntok, cudaStream_t st)
+{
+    const bool small_la = P.la <= 16;
+    const int hist_cap = (P.window + 15) & ~15;
+    constexpr int kW = 8;
+    const long long tile_bytes = (long long)kW * kSegBytes;
+    const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
+    if (n_tiles == 0) return cudaSuccess;
+    const size_t smem = bucket_parse_smem(P, kW, hist_cap, true, sizeof(uint16_t));
+    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, uint16_t>
+                         : lz77_parse_bucket_kernel<false, kW, uint16_t>;
+    cudaError_t rc =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    kern<<<(unsigned)n_tiles, kW * 32, smem, st>>>(d_in, n_in, P, hist_cap, n_tiles, tok_tmp,
+                                                   seg_ntok, (uint16_t *)nullptr, 0);
+    return cudaGetLastError();
+}
+
+}  // namespace lz77
