@@ -13,7 +13,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "liblz77b200.so"
+LIB_PATH = Path(os.environ.get("LZ77_B200_LIB", _HERE / "liblz77b200.so"))  # override: experiments only
 
 DEFAULT_LA = 15    # reference lz77.c:21
 DEFAULT_SB = 4095  # reference lz77.c:22

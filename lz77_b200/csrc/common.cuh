@@ -12,7 +12,10 @@
 
 namespace lz77 {
 
-constexpr int kSegBytes = 2048;        // greedy parse restarts every segment
+#ifndef LZ77_SEG_BYTES
+#define LZ77_SEG_BYTES 1024
+#endif
+constexpr int kSegBytes = LZ77_SEG_BYTES;  // greedy parse restarts every segment
 constexpr int kHeaderBits = 32;        // SB:16, LA:16 (lz77.c:74-75)
 
 struct Params {

@@ -35,17 +35,18 @@ __device__ __forceinline__ int bucket_key(const uint8_t *smem, int i)
 }
 
 // first index in [0, n) of the ascending list e[] whose value is >= lo (n if none);
-// warp-uniform, 32 probes per step
-template <typename PosT>
-__device__ __forceinline__ int warp_lower_bound(const PosT *e, int n, int lo, int lane)
+// uniform across the kLanes lanes of a group, kLanes probes per step
+template <int kLanes, typename PosT>
+__device__ __forceinline__ int group_lower_bound(const PosT *e, int n, int lo, int sl,
+                                                 unsigned gmask, int gshift)
 {
     int base = 0, cnt = n;
-    while (cnt > 32) {
-        const int step = (cnt + 31) >> 5;
-        const int idx = base + lane * step;
+    while (cnt > kLanes) {
+        const int step = (cnt + kLanes - 1) / kLanes;
+        const int idx = base + sl * step;
         const bool ge = idx < base + cnt ? (int)e[idx] >= lo : true;
-        const unsigned m = __ballot_sync(0xffffffffu, ge);
-        const int first = m ? __ffs(m) - 1 : 32;
+        const unsigned m = __ballot_sync(gmask, ge) >> gshift;
+        const int first = m ? __ffs(m) - 1 : kLanes;
         if (first == 0) return base;
         // the answer lies in (probe[first-1], probe[first]]
         const int nb = base + (first - 1) * step + 1;
@@ -53,13 +54,17 @@ __device__ __forceinline__ int warp_lower_bound(const PosT *e, int n, int lo, in
         base = nb;
         cnt = ne - nb;
     }
-    const int idx = base + lane;
+    const int idx = base + sl;
     const bool ge = idx < base + cnt ? (int)e[idx] >= lo : true;
-    const unsigned m = __ballot_sync(0xffffffffu, ge);
-    return base + (m ? __ffs(m) - 1 : 32);  // lanes beyond cnt report true, so <= base + cnt
+    const unsigned m = __ballot_sync(gmask, ge) >> gshift;
+    return base + (m ? __ffs(m) - 1 : kLanes);  // lanes beyond cnt report true, so <= base + cnt
 }
 
-template <bool kSmallLA, int kWarps, typename PosT>
+// kLanes lanes (a "group": 32, 16 or 8) cooperate on one parse segment, so a warp
+// parses 32 / kLanes segments side by side: the per-token scalar work (target
+// load, bucket lookup, window bound, reduction, emit) is issued once for all
+// the groups of a warp that are in step.
+template <bool kSmallLA, int kWarps, int kLanes, typename PosT, bool kSortedGlobal>
 __global__ void __launch_bounds__(kWarps * 32)
 lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
                          long long n_tiles, uint32_t *__restrict__ tok_tmp,
@@ -72,19 +77,23 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
     __shared__ uint32_t s_total;
 
     constexpr int kThreads = kWarps * 32;
+    constexpr int kSegsPerWarp = 32 / kLanes;
     constexpr int kCntWords = kBuckets * (kWarps / 2);  // two 16-bit counters per word
-    const int tile_bytes = kWarps * kSegBytes;
+    constexpr int tile_bytes = kWarps * kSegsPerWarp * kSegBytes;
     const int data_cap = hist_cap + tile_bytes + 64;
     PosT *bstart = reinterpret_cast<PosT *>(smem + ((data_cap + 15) & ~15));
     uint32_t *cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bstart) +
                                                  (((kBuckets + 1) * sizeof(PosT) + 15) & ~15));
-    PosT *sorted = sorted_global ? sorted_global + (long long)blockIdx.x * sorted_stride
+    PosT *sorted = kSortedGlobal ? sorted_global + (long long)blockIdx.x * sorted_stride
                                  : reinterpret_cast<PosT *>(cnt + kCntWords);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int cnt_col = warp >> 1, cnt_sh = (warp & 1) * 16;
+    const int sg = lane / kLanes, sl = lane % kLanes;  // group in the warp, lane in the group
+    const int gshift = sg * kLanes;
+    const unsigned gmask = kLanes == 32 ? 0xffffffffu : ((1u << (kLanes & 31)) - 1u) << gshift;
 
     if (threadIdx.x == 0) {
         mbar_init(&mbar, 1);
@@ -173,12 +182,13 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                 sorted[slot] = (PosT)i;
             }
         }
-        if (sorted_global) __threadfence_block();
+        if (kSortedGlobal) __threadfence_block();
         __syncthreads();
 
-        // ---- parse this warp's segment -----------------------------------
-        const long long seg_lo = tile_lo + (long long)warp * kSegBytes;
-        const long long sgm = tile_i * kWarps + warp;  // global segment index
+        // ---- parse: one group of kLanes lanes per segment -------------------
+        const long long seg_lo =
+            tile_lo + (long long)(warp * kSegsPerWarp + sg) * kSegBytes;
+        const long long sgm = seg_lo / kSegBytes;  // global segment index
         if (seg_lo < n) {
             long long seg_hi = seg_lo + kSegBytes;
             if (seg_hi > n) seg_hi = n;
@@ -208,10 +218,13 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     const PosT *e = sorted + bs;
                     int best_len = 0, best_q = 0;
                     // candidates: bucket entries in [lo_idx, p0), oldest first
-                    for (int i = warp_lower_bound(e, bn, lo_idx, lane); i < bn; i += 32) {
-                        const int idx = i + lane;
+                    int i = bn <= kLanes
+                                ? 0
+                                : group_lower_bound<kLanes>(e, bn, lo_idx, sl, gmask, gshift);
+                    for (; i < bn; i += kLanes) {
+                        const int idx = i + sl;
                         const int q = idx < bn ? (int)e[idx] : 0x7fffffff;
-                        if (q < p0) {
+                        if (q >= lo_idx && q < p0) {
                             // nearer than anything this lane has seen: must be longer
                             const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
                             if (l > best_len) {
@@ -219,19 +232,19 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                                 best_q = q;
                             }
                         }
-                        if (__any_sync(0xffffffffu, best_len >= max_len || q >= p0)) break;
+                        if (__any_sync(gmask, best_len >= max_len || q >= p0)) break;
                     }
                     const uint32_t k = __reduce_max_sync(
-                        0xffffffffu, best_len ? ((uint32_t)best_len << 20) |
-                                                    (0xfffffu - (uint32_t)best_q) : 0u);
+                        gmask, best_len ? ((uint32_t)best_len << 20) |
+                                              (0xfffffu - (uint32_t)best_q) : 0u);
                     len = (int)(k >> 20);
                     int q_best = (int)(0xfffffu - (k & 0xfffffu));
                     if (len < 2) {
                         // length 1: the oldest in-window position with the same first
                         // byte, in any of the 8 buckets of that byte
                         int q1 = 0x7fffffff;
-                        if (lane < 8) {
-                            const int kb = (key & ~7) + lane;
+                        if (sl < 8) {
+                            const int kb = (key & ~7) + sl;
                             const int s1 = (int)bstart[kb];
                             int lo_i = 0, hi_i = (int)bstart[kb + 1] - s1;
                             const PosT *e1 = sorted + s1;
@@ -242,7 +255,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                             }
                             if (lo_i < n1 && (int)e1[lo_i] < p0) q1 = (int)e1[lo_i];
                         }
-                        q1 = (int)__reduce_min_sync(0xffffffffu, (unsigned)q1);
+                        q1 = (int)__reduce_min_sync(gmask, (unsigned)q1);
                         if (q1 != 0x7fffffff) {
                             len = 1;
                             q_best = q1;
@@ -256,13 +269,13 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                 const uint32_t lit = smem[p0 + len];
                 const uint32_t tok =
                     (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
-                if (lane == (ntok & 31)) held = tok;
+                if (sl == (ntok & (kLanes - 1))) held = tok;
                 ntok++;
-                if ((ntok & 31) == 0) tok_out[ntok - 32 + lane] = held;  // coalesced 128 B row
+                if ((ntok & (kLanes - 1)) == 0) tok_out[ntok - kLanes + sl] = held;
                 p0 += len + 1;
             }
-            if (lane < (ntok & 31)) tok_out[(ntok & ~31) + lane] = held;
-            if (lane == 0) seg_ntok[sgm] = (uint32_t)ntok;
+            if (sl < (ntok & (kLanes - 1))) tok_out[(ntok & ~(kLanes - 1)) + sl] = held;
+            if (sl == 0) seg_ntok[sgm] = (uint32_t)ntok;
         }
         __syncthreads();  // the next tile overwrites the staged data and the buckets
     }
@@ -270,30 +283,29 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
 
 // ---------------------------------------------------------------------------
 
-size_t bucket_parse_smem(const Params &P, int nwarps, int hist_cap, bool sorted_in_smem,
-                         size_t pos_bytes)
-{
-    const size_t data_cap = (size_t)hist_cap + (size_t)nwarps * kSegBytes + 64;
-    size_t b = (data_cap + 15) & ~(size_t)15;
-    b += ((kBuckets + 1) * pos_bytes + 15) & ~(size_t)15;
-    b += (size_t)kBuckets * (nwarps / 2) * 4;
-    if (sorted_in_smem) b += data_cap * pos_bytes;
-    (void)P;
-    return b + 16;
-}
+#ifndef LZ77_PARSE_WARPS
+#define LZ77_PARSE_WARPS 8
+#endif
+#ifndef LZ77_PARSE_LANES
+#define LZ77_PARSE_LANES 32
+#endif
 
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
                                 uint32_t *tok_tmp, uint32_t *seg_ntok, cudaStream_t st)
 {
+    constexpr int kW = LZ77_PARSE_WARPS, kL = LZ77_PARSE_LANES;
     const bool small_la = P.la <= 16;
     const int hist_cap = (P.window + 15) & ~15;
-    constexpr int kW = 8;
-    const long long tile_bytes = (long long)kW * kSegBytes;
+    const long long tile_bytes = (long long)kW * (32 / kL) * kSegBytes;
     const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
     if (n_tiles == 0) return cudaSuccess;
-    const size_t smem = bucket_parse_smem(P, kW, hist_cap, true, sizeof(uint16_t));
-    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, uint16_t>
-                         : lz77_parse_bucket_kernel<false, kW, uint16_t>;
+    const size_t data_cap = (size_t)hist_cap + (size_t)tile_bytes + 64;
+    size_t smem = (data_cap + 15) & ~(size_t)15;               // staged bytes
+    smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // bucket starts
+    smem += (size_t)kBuckets * (kW / 2) * 4;                   // per-warp counters
+    smem += data_cap * sizeof(uint16_t) + 16;                  // sorted positions
+    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, kL, uint16_t, false>
+                         : lz77_parse_bucket_kernel<false, kW, kL, uint16_t, false>;
     cudaError_t rc =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
