@@ -72,7 +72,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -261,14 +261,16 @@ def run_native(args):
         t_dec = api.last_timing()
         return s, k, back, t_enc, t_dec
 
+    # nvidia-smi needs a moment to start streaming: launch it before the warm-up so
+    # it is sampling (every 50 ms) throughout both timed regions
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         s, k, back, _, _ = device_step()
     c_bytes = s.numel()
     assert torch.equal(back, src), "roundtrip mismatch"
 
     # ---- timed region: device-resident ------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     per = {"enc_search_ms": [], "enc_scan_ms": [], "enc_pack_ms": [], "dec_scan_ms": [],
            "dec_copy_ms": []}
@@ -291,7 +293,6 @@ def run_native(args):
     total_ms = ev[0].elapsed_time(ev[-1])
     enc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)) / args.steps
     dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
-    clocks = sampler.stop()
 
     # ---- timed region: end to end through the host entry points -----------
     h_in = api.PinnedBuffer(n)
@@ -311,6 +312,7 @@ def run_native(args):
     e1.record(stream_t)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
     assert m == n and bytes(h_out.array[:4096]) == bytes(h_in.array[:4096])
     assert (h_out.array[:n] == h_in.array[:n]).all(), "e2e roundtrip mismatch"
 
