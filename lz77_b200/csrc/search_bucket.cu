@@ -8,7 +8,7 @@
 // bytes, then a token only verifies the positions that share its key.
 //
 //   build (per tile, all warps)
-//     key(q) = x[q] << 3 | x[q+1] & 7                     (2048 buckets)
+//     key(q) = x[q] << 2 | x[q+1] & 3                     (1024 buckets)
 //     stable counting sort of the tile's positions by key: per-warp histogram
 //     of a contiguous chunk (packed 16-bit counters, shared-memory atomics),
 //     column scan across warps + bucket scan, then an in-order scatter whose
@@ -19,19 +19,24 @@
 //     -> 32 candidates per round, oldest first, verified against the target
 //     held in registers -> (length, oldest start) reduced with REDUX; stops at
 //     the first maximum-length match.
-//     A match of length 1 can sit in any of the 8 buckets that share the first
-//     byte; when nothing longer exists, 8 lanes binary-search those buckets for
+//     A match of length 1 can sit in any of the 4 buckets that share the first
+//     byte; when nothing longer exists, 4 lanes binary-search those buckets for
 //     the oldest in-window position.
 #include "kernels.cuh"
 #include "match.cuh"
 
 namespace lz77 {
 
-constexpr int kBuckets = 2048;
+#ifndef LZ77_KEY_LOW_BITS
+#define LZ77_KEY_LOW_BITS 2
+#endif
+constexpr int kKeyLow = LZ77_KEY_LOW_BITS;        // bits of the second byte in the key
+constexpr int kBuckets = 256 << kKeyLow;
+constexpr int kLinearScan = 128;  // buckets up to this size are scanned from their start
 
 __device__ __forceinline__ int bucket_key(const uint8_t *smem, int i)
 {
-    return ((int)smem[i] << 3) | ((int)smem[i + 1] & 7);
+    return ((int)smem[i] << kKeyLow) | ((int)smem[i + 1] & ((1 << kKeyLow) - 1));
 }
 
 // first index in [0, n) of the ascending list e[] whose value is >= lo (n if none);
@@ -195,30 +200,45 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             const int seg_end = (int)(seg_hi - src_lo) + dst0;
             int p0 = (int)(seg_lo - src_lo) + dst0;
             const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // may be < 0
-            uint32_t *tok_out = tok_tmp + sgm * kSegBytes;
+            uint32_t *tok_row = tok_tmp + sgm * kSegBytes + sl;  // this lane's slot in the row
             const int len_shift = P.ob, lit_shift = P.ob + P.lb;
+            const int la = P.la, window = P.window;
             int ntok = 0;
             uint32_t held = 0;
 
             while (p0 < seg_end) {
-                const int max_len = min(P.la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
-                const int reach = min(p0 - blk_idx, P.window);    // lz77.c:101-105
+                const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
+                const int reach = min(p0 - blk_idx, window);    // lz77.c:101-105
                 int len = 0, off = 0;
 
                 if (max_len > 0 && reach > 0) {
                     const int lo_idx = p0 - reach;
-                    uint32_t tgt[4] = {0, 0, 0, 0};
-                    if (kSmallLA) {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) tgt[i] = lds_u32_unaligned(smem, p0 + 4 * i);
+                    // lookahead: 16 bytes at p0 from five aligned words
+                    uint32_t tgt[4];
+                    {
+                        const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (p0 & ~3));
+                        const int sh = (p0 & 3) * 8;
+                        const uint32_t a0 = w[0], a1 = w[1];
+                        tgt[0] = __funnelshift_r(a0, a1, sh);
+                        if (kSmallLA) {
+                            const uint32_t a2 = w[2], a3 = w[3], a4 = w[4];
+                            tgt[1] = __funnelshift_r(a1, a2, sh);
+                            tgt[2] = __funnelshift_r(a2, a3, sh);
+                            tgt[3] = __funnelshift_r(a3, a4, sh);
+                        } else {
+                            tgt[1] = tgt[2] = tgt[3] = 0;
+                        }
                     }
-                    const int key = bucket_key(smem, p0);
+                    const int key = (int)((tgt[0] & 0xffu) << kKeyLow) |
+                                    (int)((tgt[0] >> 8) & ((1u << kKeyLow) - 1u));
                     const int bs = (int)bstart[key];
                     const int bn = (int)bstart[key + 1] - bs;
                     const PosT *e = sorted + bs;
                     int best_len = 0, best_q = 0;
-                    // candidates: bucket entries in [lo_idx, p0), oldest first
-                    int i = bn <= kLanes
+                    // candidates: bucket entries in [lo_idx, p0), oldest first; short
+                    // buckets are walked from their start, long ones from the window's
+                    // lower bound
+                    int i = bn <= kLinearScan
                                 ? 0
                                 : group_lower_bound<kLanes>(e, bn, lo_idx, sl, gmask, gshift);
                     for (; i < bn; i += kLanes) {
@@ -243,8 +263,8 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                         // length 1: the oldest in-window position with the same first
                         // byte, in any of the 8 buckets of that byte
                         int q1 = 0x7fffffff;
-                        if (sl < 8) {
-                            const int kb = (key & ~7) + sl;
+                        if (sl < (1 << kKeyLow)) {
+                            const int kb = (key & ~((1 << kKeyLow) - 1)) + sl;
                             const int s1 = (int)bstart[kb];
                             int lo_i = 0, hi_i = (int)bstart[kb + 1] - s1;
                             const PosT *e1 = sorted + s1;
@@ -256,12 +276,8 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                             if (lo_i < n1 && (int)e1[lo_i] < p0) q1 = (int)e1[lo_i];
                         }
                         q1 = (int)__reduce_min_sync(gmask, (unsigned)q1);
-                        if (q1 != 0x7fffffff) {
-                            len = 1;
-                            q_best = q1;
-                        } else {
-                            len = 0;
-                        }
+                        len = q1 != 0x7fffffff ? 1 : 0;
+                        q_best = q1;
                     }
                     off = len ? p0 - q_best : 0;
                 }
@@ -271,10 +287,13 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
                 if (sl == (ntok & (kLanes - 1))) held = tok;
                 ntok++;
-                if ((ntok & (kLanes - 1)) == 0) tok_out[ntok - kLanes + sl] = held;
+                if ((ntok & (kLanes - 1)) == 0) {  // a full row: one coalesced store
+                    *tok_row = held;
+                    tok_row += kLanes;
+                }
                 p0 += len + 1;
             }
-            if (sl < (ntok & (kLanes - 1))) tok_out[(ntok & ~(kLanes - 1)) + sl] = held;
+            if (sl < (ntok & (kLanes - 1))) *tok_row = held;
             if (sl == 0) seg_ntok[sgm] = (uint32_t)ntok;
         }
         __syncthreads();  // the next tile overwrites the staged data and the buckets
