@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/lz77_b200.h"
 #include "kernels.cuh"
 
@@ -21,6 +23,9 @@ struct Context {
     int device = -1;
     cudaStream_t stream = nullptr;      // the stream every call uses
     cudaStream_t own_stream = nullptr;  // created by init; used unless the caller sets one
+    cudaStream_t copy_in = nullptr;     // H2D / D2H streams of the chunked host path
+    cudaStream_t copy_out = nullptr;
+    unsigned long long *pinned_totals = nullptr;  // running token count per host chunk
     void *scratch = nullptr;
     size_t scratch_cap = 0;
     void *stage_in = nullptr;   // device staging for the host entry points
@@ -35,6 +40,9 @@ struct Context {
 };
 
 Context g;
+
+constexpr long long kHostChunkBytes = 32ll << 20;  // host entry points pipeline in chunks
+constexpr long long kMaxHostChunks = 4096;
 
 int fail_cuda(cudaError_t rc, const char *what)
 {
@@ -141,6 +149,9 @@ void lz77_gpu_shutdown(void)
     if (g.stage_in) cudaFree(g.stage_in);
     if (g.stage_out) cudaFree(g.stage_out);
     if (g.pinned) cudaFreeHost(g.pinned);
+    if (g.pinned_totals) cudaFreeHost(g.pinned_totals);
+    if (g.copy_in) cudaStreamDestroy(g.copy_in);
+    if (g.copy_out) cudaStreamDestroy(g.copy_out);
     cudaStreamDestroy(g.own_stream);
     g = Context();
 }
@@ -160,6 +171,9 @@ int lz77_gpu_init(int device)
     g.stream = g.own_stream;
     for (auto &e : g.ev) CK(cudaEventCreate(&e));
     CK(cudaMallocHost((void **)&g.pinned, 256));
+    CK(cudaStreamCreateWithFlags(&g.copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.copy_out, cudaStreamNonBlocking));
+    CK(cudaMallocHost((void **)&g.pinned_totals, kMaxHostChunks * sizeof(unsigned long long)));
     g.device = device;
     g.ready = true;
     memset(&g.last, 0, sizeof g.last);
@@ -268,6 +282,74 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
     if (rc) return rc;
     rc = grow(&g.stage_out, &g.stage_out_cap, o_cap + 16);
     if (rc) return rc;
+
+    // Large inputs: chunks of whole blocks flow through three streams so the H2D
+    // copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of
+    // chunk c.  The running token count stays on the device between chunks.
+    const long long granule = encode_chunk_granule();
+    long long chunk = (long long)kHostChunkBytes / granule * granule;
+    if (chunk < granule) chunk = granule;
+    const long long n_chunks = (n_in + chunk - 1) / chunk;
+    if (n_chunks >= 2 && n_chunks <= kMaxHostChunks) {
+        rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in));
+        if (rc) return rc;
+        const EncodePlan pl = encode_plan(g.scratch, n_in);
+        std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks);
+        for (long long c = 0; c < n_chunks; c++) {
+            CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        }
+        // the copy streams start after whatever the compute stream still has queued
+        CK(cudaEventRecord(g.ev[4], g.stream));
+        CK(cudaStreamWaitEvent(g.copy_in, g.ev[4], 0));
+        CK(cudaStreamWaitEvent(g.copy_out, g.ev[4], 0));
+        for (long long c = 0; c < n_chunks; c++) {
+            const long long lo = c * chunk;
+            const long long len = (lo + chunk <= n_in) ? chunk : n_in - lo;
+            CK(cudaMemcpyAsync((char *)g.stage_in + lo, in + lo, (size_t)len,
+                               cudaMemcpyHostToDevice, g.copy_in));
+            CK(cudaEventRecord(ev_in[c], g.copy_in));
+            CK(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
+            CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
+                                   (uint32_t *)g.stage_out, g.stream, nullptr));
+            CK(cudaMemcpyAsync(&g.pinned_totals[c], pl.total, 8, cudaMemcpyDeviceToHost,
+                               g.stream));
+            CK(cudaEventRecord(ev_done[c], g.stream));
+        }
+        long done_bytes = 0;
+        int result = LZ77_OK;
+        unsigned long long k = 0;
+        for (long long c = 0; c < n_chunks; c++) {
+            CK(cudaEventSynchronize(ev_done[c]));
+            k = g.pinned_totals[c];
+            const unsigned long long bits = 32ull + k * (unsigned long long)P.tbits;
+            // words below the one holding the next token's first bit are final
+            long final_bytes = c + 1 == n_chunks ? (long)((bits + 7) / 8) : (long)(bits / 32 * 4);
+            if (final_bytes > out_cap) {
+                result = LZ77_E_SPACE;
+                break;
+            }
+            if (final_bytes > done_bytes) {
+                CK(cudaStreamWaitEvent(g.copy_out, ev_done[c], 0));
+                CK(cudaMemcpyAsync(out + done_bytes, (char *)g.stage_out + done_bytes,
+                                   (size_t)(final_bytes - done_bytes), cudaMemcpyDeviceToHost,
+                                   g.copy_out));
+                done_bytes = final_bytes;
+            }
+        }
+        CK(cudaStreamSynchronize(g.copy_out));
+        CK(cudaStreamSynchronize(g.stream));
+        for (long long c = 0; c < n_chunks; c++) {
+            cudaEventDestroy(ev_in[c]);
+            cudaEventDestroy(ev_done[c]);
+        }
+        if (result != LZ77_OK) return result;
+        *n_out = done_bytes;
+        memset(&g.last, 0, sizeof g.last);
+        g.last.launches = (int)n_chunks * encode_launch_count(chunk);
+        g.last.n_tokens = (long)k;
+        return LZ77_OK;
+    }
 
     CK(cudaEventRecord(g.ev[4], g.stream));
     if (n_in > 0) CK(cudaMemcpyAsync(g.stage_in, in, (size_t)n_in, cudaMemcpyHostToDevice, g.stream));

@@ -206,7 +206,9 @@ scan_top_kernel(unsigned long long *__restrict__ partial, long long n_partial,
                 unsigned long long *__restrict__ grand_total)
 {
     __shared__ unsigned long long total;
-    unsigned long long carry = 0;
+    // *grand_total carries the token count of the chunks encoded before this one
+    unsigned long long carry = *grand_total;
+    __syncthreads();
     for (long long base = 0; base < n_partial; base += blockDim.x) {
         const long long i = base + threadIdx.x;
         const unsigned long long v = i < n_partial ? partial[i] : 0ull;
@@ -267,19 +269,28 @@ __device__ __forceinline__ uint32_t gather_word(const uint32_t *__restrict__ tok
     return val;
 }
 
+// Zeroes the LAST word of every segment.  A segment's first word is either
+// word-aligned (then it is an interior or last word) or it is the last word of
+// the segment before it -- possibly one encoded by an earlier chunk, which has
+// already OR-ed its bits in, so it must not be zeroed again.
 __global__ void lz77_pack_prepare_kernel(const uint32_t *__restrict__ seg_ntok,
                                          const unsigned long long *__restrict__ prefix,
-                                         long long n_seg, Params P, uint32_t *__restrict__ out)
+                                         long long n_seg, Params P, bool write_header,
+                                         uint32_t *__restrict__ out)
 {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0) out[0] = (uint32_t)P.sb | ((uint32_t)P.la << 16);  // lz77.c:74-75
+    if (s == 0 && write_header)
+        out[0] = (uint32_t)P.sb | ((uint32_t)P.la << 16);  // lz77.c:74-75
     if (s >= n_seg) return;
     const uint32_t nt = seg_ntok[s];
     if (!nt) return;
     const long long b0 = kHeaderBits + (long long)P.tbits * (long long)prefix[s];
     const long long b1 = b0 + (long long)P.tbits * nt;
-    out[b0 >> 5] = 0;
-    out[(b1 - 1) >> 5] = 0;
+    // (a first segment of a later chunk that ends inside the word it shares with
+    // the previous chunk leaves that word alone)
+    const bool shared_with_earlier_chunk =
+        s == 0 && !write_header && (b0 & 31) != 0 && ((b1 - 1) >> 5) == (b0 >> 5);
+    if (!shared_with_earlier_chunk) out[(b1 - 1) >> 5] = 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -355,40 +366,58 @@ int encode_parse_config(const Params &P, int *nwarps, int *hist_cap, size_t *sme
     return 0;
 }
 
-cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, void *scratch,
-                          uint32_t *d_out_words, unsigned long long **d_total_tokens,
-                          cudaStream_t st, StageEvents *ev)
+EncodePlan encode_plan(void *scratch, long long n_in_total)
 {
-    const long long n_seg = (n_in + kSegBytes - 1) / kSegBytes;
+    const long long n_seg = (n_in_total + kSegBytes - 1) / kSegBytes;
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
     char *p = (char *)scratch;
-    uint32_t *tok_tmp = (uint32_t *)carve(p, (size_t)(n_seg * kSegBytes) * sizeof(uint32_t));
-    uint32_t *seg_ntok = (uint32_t *)carve(p, (size_t)n_seg * sizeof(uint32_t));
-    unsigned long long *prefix =
-        (unsigned long long *)carve(p, (size_t)n_seg * sizeof(unsigned long long));
-    unsigned long long *partial =
-        (unsigned long long *)carve(p, (size_t)n_part * sizeof(unsigned long long));
-    unsigned long long *total = (unsigned long long *)carve(p, 8);
-    *d_total_tokens = total;
+    EncodePlan pl;
+    pl.tok_tmp = (uint32_t *)carve(p, (size_t)(n_seg * kSegBytes) * sizeof(uint32_t));
+    pl.seg_ntok = (uint32_t *)carve(p, (size_t)n_seg * sizeof(uint32_t));
+    pl.prefix = (unsigned long long *)carve(p, (size_t)n_seg * sizeof(unsigned long long));
+    pl.partial = (unsigned long long *)carve(p, (size_t)n_part * sizeof(unsigned long long));
+    pl.total = (unsigned long long *)carve(p, 8);
+    return pl;
+}
+
+long long encode_chunk_granule() { return (long long)kScanTile * kSegBytes; }
+
+// Encodes input bytes [lo, lo + n_chunk) (lo a multiple of encode_chunk_granule(),
+// hence of the block size) of a buffer whose earlier chunks were encoded by
+// earlier calls: tokens are appended behind the *pl.total tokens written so far.
+cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
+                                bool first, const Params &P, const EncodePlan &pl,
+                                uint32_t *d_out_words, cudaStream_t st, StageEvents *ev)
+{
+    const uint8_t *d_in = d_in_base + lo;
+    const long long seg0 = lo / kSegBytes;
+    const long long n_seg = (n_chunk + kSegBytes - 1) / kSegBytes;
+    const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
+    uint32_t *tok_tmp = pl.tok_tmp + seg0 * kSegBytes;
+    uint32_t *seg_ntok = pl.seg_ntok + seg0;
+    unsigned long long *prefix = pl.prefix + seg0;
+    unsigned long long *partial = pl.partial + seg0 / kScanTile;
+    unsigned long long *total = pl.total;
 
     int nwarps, hist_cap;
     size_t smem;
     encode_parse_config(P, &nwarps, &hist_cap, &smem);
     const long long tile_bytes = (long long)nwarps * kSegBytes;
-    const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
+    const long long n_tiles = (n_chunk + tile_bytes - 1) / tile_bytes;
     const bool small_la = P.la <= 16;
 
+    if (first) cudaMemsetAsync(total, 0, 8, st);
     if (ev) cudaEventRecord(ev->e[0], st);
     if (n_tiles > 0 && P.window <= 8191) {
         // small windows: bucketed search (search_bucket.cu)
-        cudaError_t rc = launch_parse_bucket(d_in, n_in, P, tok_tmp, seg_ntok, st);
+        cudaError_t rc = launch_parse_bucket(d_in, n_chunk, P, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
     } else if (n_tiles > 0) {
         auto kern = small_la ? lz77_parse_kernel<true> : lz77_parse_kernel<false>;
         cudaError_t rc =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
-        kern<<<(unsigned)n_tiles, nwarps * 32, smem, st>>>(d_in, n_in, P, hist_cap, tok_tmp,
+        kern<<<(unsigned)n_tiles, nwarps * 32, smem, st>>>(d_in, n_chunk, P, hist_cap, tok_tmp,
                                                             seg_ntok);
     }
     if (ev) cudaEventRecord(ev->e[1], st);
@@ -397,20 +426,27 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, 
         scan_top_kernel<<<1, 1024, 0, st>>>(partial, n_part, total);
         scan_apply_kernel<<<(unsigned)n_part, kScanThreads, 0, st>>>(seg_ntok, n_seg, partial,
                                                                       prefix);
-    } else {
-        cudaMemsetAsync(total, 0, 8, st);
     }
     if (ev) cudaEventRecord(ev->e[2], st);
     {
         const long long nthreads = n_seg > 0 ? n_seg : 1;
         lz77_pack_prepare_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(
-            seg_ntok, prefix, n_seg, P, d_out_words);
+            seg_ntok, prefix, n_seg, P, first, d_out_words);
         if (n_seg > 0)
             lz77_pack_kernel<<<(unsigned)((n_seg + 7) / 8), 256, 0, st>>>(
                 tok_tmp, seg_ntok, prefix, n_seg, P, d_out_words);
     }
     if (ev) cudaEventRecord(ev->e[3], st);
     return cudaGetLastError();
+}
+
+cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, void *scratch,
+                          uint32_t *d_out_words, unsigned long long **d_total_tokens,
+                          cudaStream_t st, StageEvents *ev)
+{
+    const EncodePlan pl = encode_plan(scratch, n_in);
+    *d_total_tokens = pl.total;
+    return launch_encode_chunk(d_in, 0, n_in, true, P, pl, d_out_words, st, ev);
 }
 
 int encode_launch_count(long long n_in)

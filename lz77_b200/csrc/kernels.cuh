@@ -18,6 +18,20 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, 
                           uint32_t *d_out_words, unsigned long long **d_total_tokens,
                           cudaStream_t st, StageEvents *ev);
 
+// chunked encoding (the host entry point overlaps copies with kernels)
+struct EncodePlan {
+    uint32_t *tok_tmp;
+    uint32_t *seg_ntok;
+    unsigned long long *prefix;
+    unsigned long long *partial;
+    unsigned long long *total;  // running token count (device)
+};
+EncodePlan encode_plan(void *scratch, long long n_in_total);
+long long encode_chunk_granule();
+cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
+                                bool first, const Params &P, const EncodePlan &pl,
+                                uint32_t *d_out_words, cudaStream_t st, StageEvents *ev);
+
 // bucketed longest-match search + greedy parse (search_bucket.cu)
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
                                 uint32_t *tok_tmp, uint32_t *seg_ntok, cudaStream_t st);

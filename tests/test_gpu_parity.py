@@ -211,3 +211,21 @@ def test_cli_cross_roundtrip_with_reference(lz, orc, tmp_path):
     r = subprocess.run([str(cli), "-c", "-i", str(fin), "-o", "x", "-l", "1"],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "Bad lookahead size value." in r.stderr
+
+
+@pytest.mark.parametrize("sb,la,n", [(4095, 15, 80 << 20), (1000, 20, (70 << 20) + 12_345),
+                                     (4095, 15, (64 << 20) + 3), (1, 2, (33 << 20) + 1)])
+def test_host_chunked_encode_equals_device_encode(lz, orc, sb, la, n):
+    """The host entry point pipelines inputs above 32 MiB in chunks (H2D, kernels
+    and D2H overlapped); the stream must be bit-identical to the one-shot device
+    encode, also when a chunk seam falls inside a byte (23- and 9-bit tokens)."""
+    import torch
+    from lz77_b200 import synth
+    src = synth.zipf_text(n, seed=31, device="cuda")
+    dev_stream, ntok = lz.encode_tensor(src, la=la, sb=sb)
+    host_stream = lz.encode(src.cpu().numpy(), la=la, sb=sb)
+    assert host_stream == dev_stream.cpu().numpy().tobytes()
+    assert len(host_stream) == 4 + (ntok * lz.token_bits(sb, la) + 7) // 8
+    assert lz.decode(host_stream) == src.cpu().numpy().tobytes()
+    if sb != 1:
+        assert orc.decode(host_stream[:4] + host_stream[4:]) == src.cpu().numpy().tobytes()
