@@ -231,7 +231,20 @@ def run_native(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator is
+        # created; stdout must carry exactly one JSON line, so park fd 1 on stderr
+        # until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     lz77_b200.init(local_rank)
     sb, la, n = WORKLOAD["sb"], WORKLOAD["la"], args.bytes or WORKLOAD["n"]
