@@ -84,6 +84,11 @@ const char *lz77_gpu_last_error(void);
  * Calls stay synchronous: the stream is drained before they return. */
 int  lz77_gpu_set_stream(void *cuda_stream);
 
+/* The host entry points pipeline inputs larger than this many bytes in chunks
+ * (H2D copy, kernels and D2H copy of successive chunks overlap; default 32 MiB).
+ * bytes <= 0 turns chunking off. */
+void lz77_gpu_set_host_chunk(long bytes);
+
 /* pinned host memory for fast host<->device copies (optional) */
 void *lz77_gpu_host_alloc(long n);
 void  lz77_gpu_host_free(void *p);

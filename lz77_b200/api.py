@@ -27,7 +27,7 @@ EXPORTS = (
     "lz77_gpu_strerror", "lz77_gpu_last_error", "lz77_gpu_host_alloc", "lz77_gpu_host_free",
     "lz77_gpu_encode", "lz77_gpu_decode_size", "lz77_gpu_decode", "lz77_gpu_encode_device",
     "lz77_gpu_decode_size_device", "lz77_gpu_decode_device", "lz77_gpu_last_timing",
-    "lz77_gpu_set_timing", "lz77_gpu_set_stream",
+    "lz77_gpu_set_timing", "lz77_gpu_set_stream", "lz77_gpu_set_host_chunk",
 )
 
 
@@ -87,6 +87,7 @@ def load_library() -> C.CDLL:
         "lz77_gpu_last_timing": (ip, [C.POINTER(Timing)]),
         "lz77_gpu_set_timing": (None, [ip]),
         "lz77_gpu_set_stream": (ip, [vp]),
+        "lz77_gpu_set_host_chunk": (None, [lp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -162,6 +163,11 @@ def set_stream(cuda_stream: int | None) -> None:
     """Run later calls on this CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``);
     None restores the library's own stream."""
     _check(load_library().lz77_gpu_set_stream(cuda_stream or None))
+
+
+def set_host_chunk(nbytes: int) -> None:
+    """Chunk size of the pipelined host entry points (<= 0: no chunking)."""
+    load_library().lz77_gpu_set_host_chunk(nbytes)
 
 
 def set_timing(enabled: bool) -> None:

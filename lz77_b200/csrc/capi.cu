@@ -41,7 +41,7 @@ struct Context {
 
 Context g;
 
-constexpr long long kHostChunkBytes = 32ll << 20;  // host entry points pipeline in chunks
+long long kHostChunkBytes = 32ll << 20;  // host entry points pipeline in chunks of this size
 constexpr long long kMaxHostChunks = 4096;
 
 int fail_cuda(cudaError_t rc, const char *what)
@@ -214,6 +214,12 @@ void lz77_gpu_host_free(void *p)
 
 void lz77_gpu_set_timing(int enabled) { g.timing = enabled != 0; }
 
+void lz77_gpu_set_host_chunk(long bytes)
+{
+    // <= 0: no chunking (one H2D, the kernels, one D2H); the default is 32 MiB
+    kHostChunkBytes = bytes > 0 ? bytes : (1ll << 62);
+}
+
 int lz77_gpu_set_stream(void *cuda_stream)
 {
     if (!g.ready) return LZ77_E_NODEVICE;
@@ -243,7 +249,7 @@ int lz77_gpu_encode_device(const void *d_in, long n_in, int sb, int la, void *d_
     const long bound = lz77_gpu_encode_bound(n_in, P.sb, P.la);
     if (out_cap < ((bound + 15) & ~15L)) return LZ77_E_SPACE;
     CK(cudaSetDevice(g.device));
-    int rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in));
+    int rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in, P));
     if (rc) return rc;
 
     unsigned long long *d_total = nullptr;
@@ -287,13 +293,13 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
     // copy of chunk c+1 and the D2H copy of chunk c-1 overlap the kernels of
     // chunk c.  The running token count stays on the device between chunks.
     const long long granule = encode_chunk_granule();
-    long long chunk = (long long)kHostChunkBytes / granule * granule;
+    long long chunk = kHostChunkBytes / granule * granule;
     if (chunk < granule) chunk = granule;
     const long long n_chunks = (n_in + chunk - 1) / chunk;
     if (n_chunks >= 2 && n_chunks <= kMaxHostChunks) {
-        rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in));
+        rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in, P));
         if (rc) return rc;
-        const EncodePlan pl = encode_plan(g.scratch, n_in);
+        const EncodePlan pl = encode_plan(g.scratch, n_in, P);
         std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks);
         for (long long c = 0; c < n_chunks; c++) {
             CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));

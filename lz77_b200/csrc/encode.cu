@@ -152,6 +152,12 @@ lz77_parse_kernel(const uint8_t *__restrict__ in, long long n, Params P, int his
 // token-count prefix sums (uint32 counts -> uint64 exclusive prefix)
 // ---------------------------------------------------------------------------
 
+#ifndef LZ77_EXHAUSTIVE_SCAN
+#define LZ77_EXHAUSTIVE_SCAN 0
+#endif
+// 1: large windows use the exhaustive scan above instead of search_bigwin.cu (debugging aid)
+constexpr bool kUseExhaustiveScan = LZ77_EXHAUSTIVE_SCAN != 0;
+
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
@@ -338,7 +344,9 @@ lz77_pack_kernel(const uint32_t *__restrict__ tok_tmp, const uint32_t *__restric
 // host-side launchers
 // ---------------------------------------------------------------------------
 
-size_t encode_scratch_bytes(long long n_in)
+constexpr long long kBigSuperChunk = 256ll << 20;  // large-window bucket tables cover this much
+
+size_t encode_scratch_bytes(long long n_in, const Params &P)
 {
     const long long n_seg = (n_in + kSegBytes - 1) / kSegBytes;
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
@@ -348,7 +356,9 @@ size_t encode_scratch_bytes(long long n_in)
     b += (size_t)((n_seg + 63) & ~63LL) * sizeof(unsigned long long);  // prefix
     b += (size_t)((n_part + 63) & ~63LL) * sizeof(unsigned long long); // partials
     b += 256;                                                      // grand total
-    return b + 1024;
+    if (P.window > 8191)                                           // block-level bucket tables
+        b += bigwin_scratch_bytes(n_in < kBigSuperChunk ? n_in : kBigSuperChunk, P);
+    return b + 4096;
 }
 
 static inline char *carve(char *&p, size_t bytes)
@@ -366,7 +376,7 @@ int encode_parse_config(const Params &P, int *nwarps, int *hist_cap, size_t *sme
     return 0;
 }
 
-EncodePlan encode_plan(void *scratch, long long n_in_total)
+EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P)
 {
     const long long n_seg = (n_in_total + kSegBytes - 1) / kSegBytes;
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
@@ -377,6 +387,7 @@ EncodePlan encode_plan(void *scratch, long long n_in_total)
     pl.prefix = (unsigned long long *)carve(p, (size_t)n_seg * sizeof(unsigned long long));
     pl.partial = (unsigned long long *)carve(p, (size_t)n_part * sizeof(unsigned long long));
     pl.total = (unsigned long long *)carve(p, 8);
+    pl.big = P.window > 8191 ? (void *)p : nullptr;
     return pl;
 }
 
@@ -412,6 +423,14 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
         // small windows: bucketed search (search_bucket.cu)
         cudaError_t rc = launch_parse_bucket(d_in, n_chunk, P, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
+    } else if (n_tiles > 0 && !kUseExhaustiveScan) {
+        // large windows: block-level buckets (search_bigwin.cu), a bounded range at a time
+        for (long long o = 0; o < n_chunk; o += kBigSuperChunk) {
+            const long long len = n_chunk - o < kBigSuperChunk ? n_chunk - o : kBigSuperChunk;
+            cudaError_t rc =
+                launch_parse_bigwin(d_in + o, len, P, pl.big, tok_tmp + o, seg_ntok + o / kSegBytes, st);
+            if (rc != cudaSuccess) return rc;
+        }
     } else if (n_tiles > 0) {
         auto kern = small_la ? lz77_parse_kernel<true> : lz77_parse_kernel<false>;
         cudaError_t rc =
@@ -444,7 +463,7 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, 
                           uint32_t *d_out_words, unsigned long long **d_total_tokens,
                           cudaStream_t st, StageEvents *ev)
 {
-    const EncodePlan pl = encode_plan(scratch, n_in);
+    const EncodePlan pl = encode_plan(scratch, n_in, P);
     *d_total_tokens = pl.total;
     return launch_encode_chunk(d_in, 0, n_in, true, P, pl, d_out_words, st, ev);
 }

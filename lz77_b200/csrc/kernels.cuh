@@ -10,7 +10,7 @@ struct StageEvents {
 };
 
 // ---- encoder (encode.cu) ---------------------------------------------------
-size_t encode_scratch_bytes(long long n_in);
+size_t encode_scratch_bytes(long long n_in, const Params &P);
 int encode_launch_count(long long n_in);
 // d_out_words must hold 4 + ceil(n_in * T / 8) bytes rounded up to 16.
 // *d_total_tokens receives a device pointer (inside scratch) to the token count.
@@ -25,8 +25,9 @@ struct EncodePlan {
     unsigned long long *prefix;
     unsigned long long *partial;
     unsigned long long *total;  // running token count (device)
+    void *big;                  // large-window bucket tables (search_bigwin.cu)
 };
-EncodePlan encode_plan(void *scratch, long long n_in_total);
+EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P);
 long long encode_chunk_granule();
 cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
                                 bool first, const Params &P, const EncodePlan &pl,
@@ -35,6 +36,12 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
 // bucketed longest-match search + greedy parse (search_bucket.cu)
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
                                 uint32_t *tok_tmp, uint32_t *seg_ntok, cudaStream_t st);
+
+// large windows: block-level buckets (search_bigwin.cu)
+size_t bigwin_scratch_bytes(long long n_in, const Params &P);
+cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Params &P,
+                                void *scratch, uint32_t *tok_tmp, uint32_t *seg_ntok,
+                                cudaStream_t st);
 
 // ---- decoder (decode.cu) ---------------------------------------------------
 struct DecodeInfo {            // lives in device scratch, copied back by the C ABI

@@ -1,0 +1,384 @@
+// search_bigwin.cu -- bucketed longest-match search for large windows
+// (SB > 8191, e.g. -s 65535 -l 255), sm_100a.
+//
+// The per-tile bucket build of search_bucket.cu does not fit shared memory when
+// the window is 64 KiB, so the buckets are built once per independent block
+// (128 KiB) into HBM / L2 and shared by all the tiles of the block:
+//
+//   lz77_block_sort_kernel   one CTA per block.  The block is staged into shared
+//       memory with one TMA bulk copy, then its positions are sorted by
+//       key = x[q] << 5 | x[q+1] & 31 (8192 buckets) with a stable two-pass LSD
+//       radix sort (digit x[q+1]&31, then digit x[q]); per-warp digit counters
+//       + MATCH.ANY ranks keep every bucket in ascending position order.
+//       Output: sorted positions (uint32) and 8193 bucket starts per block.
+//   lz77_parse_bigwin_kernel one CTA (16 warps) per 16 KiB tile: TMA-stages up to
+//       64 KiB of history + the tile, then warp w parses segment w exactly like
+//       search_bucket.cu, reading its candidates from the block's bucket lists:
+//       warp-ary lower bound of the window start, 32 candidates per round
+//       verified against shared memory, REDUX of (length, oldest start).
+//       A length-1 match (any bucket of the first byte) is found by a forward
+//       SWAR scan of the staged window from its oldest byte.
+//
+// Same result as the exhaustive scan in encode.cu (tests compare both against
+// the oracle byte for byte).
+#include "kernels.cuh"
+#include "match.cuh"
+
+namespace lz77 {
+
+constexpr int kBigKeyLow = 5;
+constexpr int kBigBuckets = 256 << kBigKeyLow;  // 8192
+constexpr int kSortThreads = 1024;
+constexpr int kSortWarps = kSortThreads / 32;
+
+// ---------------------------------------------------------------------------
+// per-block stable sort of positions by key
+// ---------------------------------------------------------------------------
+
+// One stable counting-sort pass over n elements.  Element i is src[i] (or i when
+// src == nullptr); its digit comes from digit_of(element).  Warp w handles the
+// contiguous run [w*chunk, (w+1)*chunk) so that equal digits keep their order.
+template <int kBins, typename DigitFn>
+__device__ __forceinline__ void radix_pass(const uint32_t *src, uint32_t *dst, int n,
+                                           uint32_t *cnt /* [kSortWarps][kBins] */,
+                                           uint32_t *bin_start /* [kBins + 1] */,
+                                           uint32_t *s_warp, uint32_t *s_total, DigitFn digit_of)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int rows = (n + kSortThreads - 1) / kSortThreads;
+    const int cbase = warp * rows * 32;
+    const int cend = min(n, cbase + rows * 32);
+
+    for (int i = threadIdx.x; i < kSortWarps * kBins; i += kSortThreads) cnt[i] = 0u;
+    __syncthreads();
+    for (int i = cbase + lane; i < cend; i += 32) {
+        const uint32_t el = src ? src[i] : (uint32_t)i;
+        atomicAdd(&cnt[warp * kBins + digit_of(el)], 1u);
+    }
+    __syncthreads();
+    // exclusive scan down the warps of every bin, then across the bins
+    uint32_t tot = 0;
+    if (threadIdx.x < kBins) {
+        for (int w = 0; w < kSortWarps; w++) {
+            const uint32_t v = cnt[w * kBins + threadIdx.x];
+            cnt[w * kBins + threadIdx.x] = tot;
+            tot += v;
+        }
+    }
+    const uint32_t base = block_exclusive_scan_u32<kSortThreads>(tot, s_warp, s_total);
+    if (threadIdx.x < kBins) bin_start[threadIdx.x] = base;
+    if (threadIdx.x == kBins) bin_start[kBins] = *s_total;
+    __syncthreads();
+    for (int r = 0; r < rows; r++) {
+        const int i = cbase + r * 32 + lane;
+        const bool valid = i < cend;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const uint32_t el = src ? src[i] : (uint32_t)i;
+            const int d = digit_of(el);
+            const unsigned peers = __match_any_sync(vmask, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader) old = atomicAdd(&cnt[warp * kBins + d], (uint32_t)__popc(peers));
+            old = __shfl_sync(peers, old, leader);
+            dst[bin_start[d] + old + __popc(peers & lt_mask)] = el;
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSortThreads, 1)
+lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_shift,
+                       uint32_t *__restrict__ sorted, uint32_t *__restrict__ tmp,
+                       uint32_t *__restrict__ bstart)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t bin_start[257];
+
+    const long long block_bytes = 1LL << block_shift;
+    const long long blk_lo = (long long)blockIdx.x << block_shift;
+    const int nb = (int)min(block_bytes, n - blk_lo);
+    uint8_t *data = smem;                                                  // block bytes + pad
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem + block_bytes + 64); // [32][256]
+    uint32_t *cnt2 = cnt + kSortWarps * 256;                               // [8192] bucket sizes
+    uint32_t *my_sorted = sorted + blk_lo;
+    uint32_t *my_tmp = tmp + blk_lo;
+    uint32_t *my_bstart = bstart + (long long)blockIdx.x * (kBigBuckets + 1);
+
+    const int bulk = nb & ~15;
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bulk > 0) {
+        mbar_expect_tx(&mbar, (uint32_t)bulk);
+        tma_load_1d(data, in + blk_lo, (uint32_t)bulk, &mbar);
+    }
+    for (int i = bulk + threadIdx.x; i < nb + 64; i += kSortThreads)
+        data[i] = i < nb ? in[blk_lo + i] : (uint8_t)0;
+    for (int i = threadIdx.x; i < kBigBuckets; i += kSortThreads) cnt2[i] = 0u;
+    if (bulk > 0) mbar_wait(&mbar, 0);
+    __syncthreads();
+
+    // bucket sizes (for the bucket start table)
+    for (int i = threadIdx.x; i < nb; i += kSortThreads)
+        atomicAdd(&cnt2[((int)data[i] << kBigKeyLow) | (data[i + 1] & ((1 << kBigKeyLow) - 1))],
+                  1u);
+    // pass 1: low digit = x[q+1] & 31 ; pass 2: high digit = x[q]
+    radix_pass<1 << kBigKeyLow>(nullptr, my_tmp, nb, cnt, bin_start, s_warp, &s_total,
+                                [&](uint32_t q) { return (int)(data[q + 1] & ((1 << kBigKeyLow) - 1)); });
+    radix_pass<256>(my_tmp, my_sorted, nb, cnt, bin_start, s_warp, &s_total,
+                    [&](uint32_t q) { return (int)data[q]; });
+    // bucket starts: exclusive scan of the 8192 bucket sizes
+    {
+        constexpr int per = kBigBuckets / kSortThreads;  // 8
+        uint32_t v[per], sum = 0;
+#pragma unroll
+        for (int b = 0; b < per; b++) {
+            v[b] = cnt2[threadIdx.x * per + b];
+            sum += v[b];
+        }
+        uint32_t base = block_exclusive_scan_u32<kSortThreads>(sum, s_warp, &s_total);
+#pragma unroll
+        for (int b = 0; b < per; b++) {
+            my_bstart[threadIdx.x * per + b] = base;
+            base += v[b];
+        }
+        if (threadIdx.x == kSortThreads - 1) my_bstart[kBigBuckets] = base;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// parse with block-level buckets
+// ---------------------------------------------------------------------------
+
+// first index in [0, n) of the ascending list e[] whose value is >= lo (n if none)
+__device__ __forceinline__ int warp_lower_bound_g(const uint32_t *__restrict__ e, int n, int lo,
+                                                  int lane)
+{
+    int base = 0, cnt = n;
+    while (cnt > 32) {
+        const int step = (cnt + 31) >> 5;
+        const int idx = base + lane * step;
+        const bool ge = idx < base + cnt ? (int)__ldg(e + idx) >= lo : true;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        const int first = m ? __ffs(m) - 1 : 32;
+        if (first == 0) return base;
+        const int nb = base + (first - 1) * step + 1;
+        const int ne = min(base + cnt, base + first * step + 1);
+        base = nb;
+        cnt = ne - nb;
+    }
+    const int idx = base + lane;
+    const bool ge = idx < base + cnt ? (int)__ldg(e + idx) >= lo : true;
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    return base + (m ? __ffs(m) - 1 : 32);
+}
+
+constexpr int kBigWarps = 16;
+
+template <bool kSmallLA>
+__global__ void __launch_bounds__(kBigWarps * 32, 2)
+lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
+                         const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ bstart,
+                         uint32_t *__restrict__ tok_tmp, uint32_t *__restrict__ seg_ntok)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    constexpr int kThreads = kBigWarps * 32;
+    constexpr int tile_bytes = kBigWarps * kSegBytes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long tile_lo = (long long)blockIdx.x * tile_bytes;
+    const long long blk_i = tile_lo >> P.block_shift;
+    const long long blk_lo = blk_i << P.block_shift;
+
+    long long hist = tile_lo - blk_lo;
+    if (hist > P.window) hist = P.window;
+    const int hist_al = (int)((hist + 15) & ~15LL);
+    const long long src_lo = tile_lo - hist_al;
+    long long src_hi = tile_lo + tile_bytes;
+    if (src_hi > n) src_hi = n;
+    const int bytes = (int)(src_hi - src_lo);
+    const int bulk = bytes & ~15;
+    const int dst0 = hist_cap - hist_al;  // smem index of global byte src_lo
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bulk > 0) {
+        mbar_expect_tx(&mbar, (uint32_t)bulk);
+        tma_load_1d(smem + dst0, in + src_lo, (uint32_t)bulk, &mbar);
+    }
+    for (int i = bulk + threadIdx.x; i < bytes + 64; i += kThreads)
+        smem[dst0 + i] = (i < bytes) ? in[src_lo + i] : (uint8_t)0;
+    if (bulk > 0) mbar_wait(&mbar, 0);
+    __syncthreads();
+
+    const long long seg_lo = tile_lo + (long long)warp * kSegBytes;
+    if (seg_lo >= n) return;
+    const long long sgm = seg_lo / kSegBytes;
+    long long seg_hi = seg_lo + kSegBytes;
+    if (seg_hi > n) seg_hi = n;
+    const int seg_end = (int)(seg_hi - src_lo) + dst0;
+    int p0 = (int)(seg_lo - src_lo) + dst0;
+    const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // smem index of block byte 0 (may be < 0)
+    const uint32_t *blk_sorted = sorted + blk_lo;
+    const uint32_t *blk_bstart = bstart + blk_i * (kBigBuckets + 1);
+    uint32_t *tok_row = tok_tmp + sgm * kSegBytes + lane;
+    const int len_shift = P.ob, lit_shift = P.ob + P.lb;
+    const int la = P.la, window = P.window;
+    int ntok = 0;
+    uint32_t held = 0;
+
+    while (p0 < seg_end) {
+        const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
+        const int reach = min(p0 - blk_idx, window);    // lz77.c:101-105
+        int len = 0, off = 0;
+
+        if (max_len > 0 && reach > 0) {
+            const int lo_idx = p0 - reach;
+            uint32_t tgt[4];
+            {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (p0 & ~3));
+                const int sh = (p0 & 3) * 8;
+                const uint32_t a0 = w[0], a1 = w[1];
+                tgt[0] = __funnelshift_r(a0, a1, sh);
+                if (kSmallLA) {
+                    const uint32_t a2 = w[2], a3 = w[3], a4 = w[4];
+                    tgt[1] = __funnelshift_r(a1, a2, sh);
+                    tgt[2] = __funnelshift_r(a2, a3, sh);
+                    tgt[3] = __funnelshift_r(a3, a4, sh);
+                } else {
+                    tgt[1] = tgt[2] = tgt[3] = 0;
+                }
+            }
+            const uint32_t b0 = tgt[0] & 0xffu;
+            int best_len = 0, best_q = 0;
+            if (max_len >= 2) {
+                const int key = (int)(b0 << kBigKeyLow) |
+                                (int)((tgt[0] >> 8) & ((1u << kBigKeyLow) - 1u));
+                const int bs = (int)__ldg(blk_bstart + key);
+                const int bn = (int)__ldg(blk_bstart + key + 1) - bs;
+                const uint32_t *e = blk_sorted + bs;
+                // bucket entries are positions in the block; smem index = entry + blk_idx
+                const int lo_blk = lo_idx - blk_idx, p_blk = p0 - blk_idx;
+                int i = bn <= 64 ? 0 : warp_lower_bound_g(e, bn, lo_blk, lane);
+                for (; i < bn; i += 32) {
+                    const int idx = i + lane;
+                    const int qb = idx < bn ? (int)__ldg(e + idx) : 0x7fffffff;
+                    if (qb >= lo_blk && qb < p_blk) {
+                        const int q = qb + blk_idx;
+                        const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
+                        if (l > best_len) {
+                            best_len = l;
+                            best_q = q;
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, best_len >= max_len || qb >= p_blk)) break;
+                }
+            }
+            const uint32_t k = __reduce_max_sync(
+                0xffffffffu,
+                best_len ? ((uint32_t)best_len << 20) | (0xfffffu - (uint32_t)best_q) : 0u);
+            len = (int)(k >> 20);
+            int q_best = (int)(0xfffffu - (k & 0xfffffu));
+            if (len < 2) {
+                // length 1: the oldest byte of the window equal to the first lookahead
+                // byte -- forward SWAR scan of the staged window, 512 bytes per step
+                const uint32_t b0x4 = b0 * 0x01010101u;
+                int q1 = 0x7fffffff;
+                for (int base = lo_idx & ~15; base < p0; base += 512) {
+                    const int g = base + lane * 16;
+                    if (g < p0) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(smem + g);
+                        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 3; i >= 0; i--) {
+                            uint32_t m = zero_bytes(wv[i] ^ b0x4);
+                            while (m) {
+                                const int bit = __ffs(m) - 1;
+                                m ^= 1u << bit;
+                                const int q = g + 4 * i + (bit >> 3);
+                                if (q >= lo_idx && q < p0 && q < q1) q1 = q;
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, q1 != 0x7fffffff)) break;
+                }
+                q1 = (int)__reduce_min_sync(0xffffffffu, (unsigned)q1);
+                len = q1 != 0x7fffffff ? 1 : 0;
+                q_best = q1;
+            }
+            off = len ? p0 - q_best : 0;
+        }
+
+        const uint32_t lit = smem[p0 + len];
+        const uint32_t tok = (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
+        if (lane == (ntok & 31)) held = tok;
+        ntok++;
+        if ((ntok & 31) == 0) {
+            *tok_row = held;
+            tok_row += 32;
+        }
+        p0 += len + 1;
+    }
+    if (lane < (ntok & 31)) *tok_row = held;
+    if (lane == 0) seg_ntok[sgm] = (uint32_t)ntok;
+}
+
+// ---------------------------------------------------------------------------
+
+size_t bigwin_scratch_bytes(long long n_in, const Params &P)
+{
+    const long long n_blocks = (n_in + P.block - 1) >> P.block_shift;
+    const long long npos = n_blocks << P.block_shift;
+    return (size_t)npos * 4 * 2 + (size_t)n_blocks * (kBigBuckets + 1) * 4 + 4096;
+}
+
+// d_in points at a block boundary; the scratch holds the sorted positions, the
+// radix ping buffer and the bucket start tables for [0, n_in).
+cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Params &P,
+                                void *scratch, uint32_t *tok_tmp, uint32_t *seg_ntok,
+                                cudaStream_t st)
+{
+    if (n_in <= 0) return cudaSuccess;
+    const long long n_blocks = (n_in + P.block - 1) >> P.block_shift;
+    const long long npos = n_blocks << P.block_shift;
+    uint32_t *sorted = (uint32_t *)scratch;
+    uint32_t *tmp = sorted + npos;
+    uint32_t *bstart = tmp + npos;
+
+    {
+        const size_t smem = (size_t)P.block + 64 + (size_t)kSortWarps * 256 * 4 +
+                            (size_t)kBigBuckets * 4;
+        cudaError_t rc = cudaFuncSetAttribute(
+            lz77_block_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return rc;
+        lz77_block_sort_kernel<<<(unsigned)n_blocks, kSortThreads, smem, st>>>(
+            d_in, n_in, P.block_shift, sorted, tmp, bstart);
+    }
+    {
+        const int hist_cap = (P.window + 15) & ~15;
+        const long long tile_bytes = (long long)kBigWarps * kSegBytes;
+        const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
+        const size_t smem = (size_t)hist_cap + (size_t)tile_bytes + 128;
+        auto kern = P.la <= 16 ? lz77_parse_bigwin_kernel<true> : lz77_parse_bigwin_kernel<false>;
+        cudaError_t rc =
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return rc;
+        kern<<<(unsigned)n_tiles, kBigWarps * 32, smem, st>>>(d_in, n_in, P, hist_cap, sorted,
+                                                              bstart, tok_tmp, seg_ntok);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace lz77
