@@ -326,13 +326,24 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
             // token and sources entirely inside the tile: the common, cheap copy
             const bool fast = pos_rel >= 0 && s_rel >= 0 && pos_rel + len <= tile_len;
             bool ready = false;  // sources final, copy still to do
+            // in-tile sources of at most 32 bytes: one 64-bit window of the ready bitmap
+            const int nsrc = e_rel - chk;
+            const bool fastpoll = nsrc <= 32;
+            const int pw = chk >> 5, psh = chk & 31;
+            const uint32_t pmask = nsrc >= 32 ? 0xffffffffu : nsrc <= 0 ? 0u : (1u << nsrc) - 1u;
+            const volatile uint32_t *vbits = ready_bits;
             unsigned prev_rm = 0;
             int spins = 0;
             while (true) {
                 const unsigned um = __ballot_sync(0xffffffffu, pending);
                 if (!um) break;
                 if (pending && !ready) {  // cheap poll of the ready bitmap
-                    ready = ready_test(ready_bits, chk, e_rel);
+                    if (fastpoll) {
+                        const uint32_t lo = vbits[pw], hi = vbits[pw + 1];
+                        ready = (__funnelshift_r(lo, hi, psh) & pmask) == pmask;
+                    } else {
+                        ready = ready_test(ready_bits, chk, e_rel);
+                    }
                     if (ready && ext) {
                         ready = ld_acquire_u32(&tile_done[ta]) != 0u &&
                                 ld_acquire_u32(&tile_done[tb]) != 0u;
@@ -471,7 +482,7 @@ cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
     const long long n_words = (n_in_bytes + 3) / 4;
     if (n_tiles == 0) return cudaSuccess;
     const size_t smem = (size_t)tile_bytes + ((size_t)(tile_bytes >> 5) + 8) * 4 +
-                        (size_t)(tile_bytes >> 3);  // tile + group offsets + ready bitmap
+                        (size_t)(tile_bytes >> 3) + 16;  // tile + group offsets + ready bitmap
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
