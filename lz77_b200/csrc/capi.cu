@@ -25,6 +25,7 @@ struct Context {
     cudaStream_t own_stream = nullptr;  // created by init; used unless the caller sets one
     cudaStream_t copy_in = nullptr;     // H2D / D2H streams of the chunked host path
     cudaStream_t copy_out = nullptr;
+    cudaStream_t aux = nullptr;         // second compute stream (chunked decode)
     unsigned long long *pinned_totals = nullptr;  // running token count per host chunk
     void *scratch = nullptr;
     size_t scratch_cap = 0;
@@ -152,6 +153,7 @@ void lz77_gpu_shutdown(void)
     if (g.pinned_totals) cudaFreeHost(g.pinned_totals);
     if (g.copy_in) cudaStreamDestroy(g.copy_in);
     if (g.copy_out) cudaStreamDestroy(g.copy_out);
+    if (g.aux) cudaStreamDestroy(g.aux);
     cudaStreamDestroy(g.own_stream);
     g = Context();
 }
@@ -173,6 +175,7 @@ int lz77_gpu_init(int device)
     CK(cudaMallocHost((void **)&g.pinned, 256));
     CK(cudaStreamCreateWithFlags(&g.copy_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_out, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.aux, cudaStreamNonBlocking));
     CK(cudaMallocHost((void **)&g.pinned_totals, kMaxHostChunks * sizeof(unsigned long long)));
     g.device = device;
     g.ready = true;
@@ -432,6 +435,129 @@ int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_toke
 
 }  // namespace
 
+namespace {
+
+constexpr long long kMaxDecodeChunks = 48;  // one ticket slot per tile launch (decode.cu)
+
+// Host decode of a large stream as a pipeline over chunks of the compressed
+// input: the H2D copy of chunk c+1, the token scan of chunk c, the tile decode
+// of the output tiles chunk c completed and the D2H copy of the tiles before
+// them all run concurrently (copy_in / compute / aux / copy_out streams).  The
+// stage_in buffer has already been sized by the caller.
+int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, long out_cap,
+                     long *n_out, long long n_chunks)
+{
+    Params P;
+    long long K = 0;
+    int rc = read_header(in, n_in, &P, &K);
+    if (rc) return rc;
+    memset(&g.last, 0, sizeof g.last);
+    g.last.n_tokens = (long)K;
+    if (K == 0) {
+        *n_out = 0;
+        return LZ77_OK;
+    }
+    const long long tile_bytes = 1LL << P.block_shift;
+    long long max_out = K << P.lb;  // len + 1 <= 2^lb
+    if (max_out > out_cap) max_out = out_cap;
+    const size_t o_cap = (((size_t)max_out + tile_bytes) + 15) & ~(size_t)15;
+    rc = grow(&g.stage_out, &g.stage_out_cap, o_cap + 16);
+    if (rc) return rc;
+    rc = grow(&g.scratch, &g.scratch_cap, decode_scratch_bytes(K, P));
+    if (rc) return rc;
+
+    std::vector<cudaEvent_t> ev_in(n_chunks), ev_scan(n_chunks), ev_tiles(n_chunks);
+    for (long long c = 0; c < n_chunks; c++) {
+        CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_scan[c], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_tiles[c], cudaEventDisableTiming));
+    }
+    const size_t in_cap = ((size_t)n_in + 15) & ~(size_t)15;
+    CK(cudaMemsetAsync((char *)g.stage_in + (in_cap - 16), 0, 32, g.stream));
+    CK(cudaEventRecord(g.ev[4], g.stream));
+    CK(cudaStreamWaitEvent(g.copy_in, g.ev[4], 0));
+    CK(cudaStreamWaitEvent(g.copy_out, g.ev[4], 0));
+    CK(cudaStreamWaitEvent(g.aux, g.ev[4], 0));
+
+    // queue every H2D copy and every scan; the scans need nothing from the host
+    const long long granule = decode_scan_granule();
+    DecodeInfo *d_info = nullptr;
+    long long tok_lo = 0;
+    for (long long c = 0; c < n_chunks; c++) {
+        const long long lo = c * kHostChunkBytes;
+        const long long hi = (c + 1 == n_chunks) ? n_in : lo + kHostChunkBytes;
+        CK(cudaMemcpyAsync((char *)g.stage_in + lo, in + lo, (size_t)(hi - lo),
+                           cudaMemcpyHostToDevice, g.copy_in));
+        CK(cudaEventRecord(ev_in[c], g.copy_in));
+        CK(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
+        long long tok_hi = K;
+        if (c + 1 < n_chunks) {
+            tok_hi = ((hi - 4) * 8) / P.tbits / granule * granule;  // whole tokens, whole scan chunks
+            if (tok_hi < tok_lo) tok_hi = tok_lo;
+        }
+        CK(launch_decode_scan_range((const uint32_t *)g.stage_in, hi, K, tok_lo, tok_hi, P,
+                                    g.scratch, &d_info, g.stream));
+        tok_lo = tok_hi;
+        CK(cudaMemcpyAsync(&g.pinned_totals[c], &d_info->n_out, 8, cudaMemcpyDeviceToHost,
+                           g.stream));
+        CK(cudaEventRecord(ev_scan[c], g.stream));
+    }
+
+    // as the scans finish: decode the tiles they completed, copy them back
+    long long tiles_done = 0, n_total = 0;
+    int result = LZ77_OK;
+    for (long long c = 0; c < n_chunks; c++) {
+        CK(cudaEventSynchronize(ev_scan[c]));
+        const long long pos = (long long)g.pinned_totals[c];
+        const bool last = c + 1 == n_chunks;
+        long long tile_end;
+        if (last) {
+            n_total = pos;
+            if (pos > out_cap) {
+                result = LZ77_E_SPACE;
+                break;
+            }
+            tile_end = (pos + tile_bytes - 1) >> P.block_shift;
+        } else {
+            tile_end = pos > 0 ? (pos - 1) >> P.block_shift : 0;  // tiles wholly scanned
+            const long long cap_tiles = (long long)(max_out >> P.block_shift);
+            if (tile_end > cap_tiles) tile_end = cap_tiles;        // never past the caller's buffer
+            if (tile_end < tiles_done) tile_end = tiles_done;
+        }
+        if (tile_end > tiles_done) {
+            CK(cudaStreamWaitEvent(g.aux, ev_scan[c], 0));
+            CK(launch_decode_tiles_range((const uint32_t *)g.stage_in, n_in, K, tiles_done,
+                                         tile_end, last, pos, (int)c, P, g.scratch,
+                                         (uint8_t *)g.stage_out, g.aux));
+            CK(cudaEventRecord(ev_tiles[c], g.aux));
+            CK(cudaStreamWaitEvent(g.copy_out, ev_tiles[c], 0));
+            const long long b_lo = tiles_done << P.block_shift;
+            long long b_hi = tile_end << P.block_shift;
+            if (last && b_hi > pos) b_hi = pos;
+            CK(cudaMemcpyAsync(out + b_lo, (char *)g.stage_out + b_lo, (size_t)(b_hi - b_lo),
+                               cudaMemcpyDeviceToHost, g.copy_out));
+            tiles_done = tile_end;
+        }
+    }
+    CK(cudaStreamSynchronize(g.aux));
+    CK(cudaStreamSynchronize(g.copy_out));
+    CK(cudaStreamSynchronize(g.stream));
+    if (result == LZ77_OK) {
+        CK(cudaMemcpy(g.pinned, d_info, sizeof(DecodeInfo), cudaMemcpyDeviceToHost));
+        if (((const DecodeInfo *)g.pinned)->error) result = LZ77_E_STREAM;
+    }
+    for (long long c = 0; c < n_chunks; c++) {
+        cudaEventDestroy(ev_in[c]);
+        cudaEventDestroy(ev_scan[c]);
+        cudaEventDestroy(ev_tiles[c]);
+    }
+    *n_out = n_total;
+    g.last.launches = (int)(2 * n_chunks);
+    return result;
+}
+
+}  // namespace
+
 int lz77_gpu_decode_size_device(const void *d_in, long n_in, long *n_out)
 {
     Params P;
@@ -488,6 +614,12 @@ int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long
     const size_t in_cap = ((size_t)n_in + 15) & ~(size_t)15;
     int rc = grow(&g.stage_in, &g.stage_in_cap, in_cap + 16);
     if (rc) return rc;
+    {
+        // large streams: chunked pipeline (see decode_pipelined)
+        const long long n_chunks = (n_in + kHostChunkBytes - 1) / kHostChunkBytes;
+        if (n_chunks >= 2 && n_chunks <= kMaxDecodeChunks && out)
+            return decode_pipelined(in, n_in, out, out_cap, n_out, n_chunks);
+    }
     CK(cudaEventRecord(g.ev[4], g.stream));
     CK(cudaMemsetAsync((char *)g.stage_in + (in_cap - 16), 0, 32, g.stream));
     CK(cudaMemcpyAsync(g.stage_in, in, (size_t)n_in, cudaMemcpyHostToDevice, g.stream));

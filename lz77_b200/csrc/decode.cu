@@ -200,9 +200,9 @@ template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
                         Params P, int tile_shift, const long long *__restrict__ tile_tok,
-                        const long long *__restrict__ tile_pos, long long n_tiles,
-                        long long n_out, uint8_t *out, unsigned int *tile_done,
-                        unsigned int *tickets, DecodeInfo *info)
+                        const long long *__restrict__ tile_pos, long long tile_begin,
+                        long long tile_end, long long n_tiles, long long n_out, uint8_t *out,
+                        unsigned int *tile_done, unsigned int *ticket, DecodeInfo *info)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int kWarps = kThreads / 32;
@@ -226,12 +226,12 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
 
     while (true) {
         if (threadIdx.x == 0) {
-            s_tile = atomicAdd(&tickets[1], 1u);  // tiles start in order
+            s_tile = tile_begin + atomicAdd(ticket, 1u);  // tiles start in order
             s_next_group = 0;
         }
         __syncthreads();
         const long long j = s_tile;
-        if (j >= n_tiles) break;
+        if (j >= tile_end) break;
 
         const long long tile_lo = j << tile_shift;
         long long tile_hi = tile_lo + tile_bytes;
@@ -454,33 +454,60 @@ size_t decode_scratch_bytes(long long n_tokens, const Params &P)
 
 int decode_launch_count(bool with_copy) { return with_copy ? 2 : 1; }
 
-cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
-                               long long n_tokens, const Params &P, void *scratch,
-                               DecodeInfo **d_info, cudaStream_t st)
+// Pass 1 over tokens [tok_begin, tok_end) of a stream of n_tokens tokens, of which
+// the first n_in_bytes bytes are resident.  tok_begin must be a multiple of the
+// scan chunk; the first call (tok_begin == 0) zeroes the state.  After the call
+// info->n_out holds the output position behind token tok_end - 1.
+cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_bytes,
+                                     long long n_tokens, long long tok_begin, long long tok_end,
+                                     const Params &P, void *scratch, DecodeInfo **d_info,
+                                     cudaStream_t st)
 {
     DecodeScratch s = carve_decode(scratch, n_tokens, P);
     *d_info = s.info;
-    cudaError_t rc = cudaMemsetAsync(scratch, 0, s.zero_bytes, st);
-    if (rc != cudaSuccess) return rc;
-    const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
+    if (tok_begin == 0) {
+        cudaError_t rc = cudaMemsetAsync(scratch, 0, s.zero_bytes, st);
+        if (rc != cudaSuccess) return rc;
+    }
+    const long long n_chunks = (tok_end - tok_begin + kDsChunk - 1) / kDsChunk;
     const long long n_words = (n_in_bytes + 3) / 4;
     if (n_chunks > 0)
         lz77_decode_scan_kernel<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(
-            d_in_words, n_words, n_tokens, P, P.block_shift, s.status, s.tile_tok, s.tile_pos,
+            d_in_words, n_words, tok_end, P, P.block_shift, s.status, s.tile_tok, s.tile_pos,
             s.tickets, s.info);
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
-                               long long n_tokens, long long n_out, const Params &P,
-                               void *scratch, uint8_t *d_out, cudaStream_t st)
+long long decode_scan_granule() { return kDsChunk; }
+
+cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
+                               long long n_tokens, const Params &P, void *scratch,
+                               DecodeInfo **d_info, cudaStream_t st)
+{
+    return launch_decode_scan_range(d_in_words, n_in_bytes, n_tokens, 0, n_tokens, P, scratch,
+                                    d_info, st);
+}
+
+// Pass 2 over output tiles [tile_begin, tile_end).  `last` is false for a partial
+// run of a chunked decode: then every tile of the range is complete and the
+// token that starts tile_end has been scanned; launch_idx (< 60) selects the
+// ticket slot of this launch.
+cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in_bytes,
+                                      long long n_tokens, long long tile_begin,
+                                      long long tile_end, bool last, long long n_out,
+                                      int launch_idx, const Params &P, void *scratch,
+                                      uint8_t *d_out, cudaStream_t st)
 {
     DecodeScratch s = carve_decode(scratch, n_tokens, P);
     const int tile_shift = P.block_shift;
     const long long tile_bytes = 1LL << tile_shift;
-    const long long n_tiles = (n_out + tile_bytes - 1) >> tile_shift;
     const long long n_words = (n_in_bytes + 3) / 4;
-    if (n_tiles == 0) return cudaSuccess;
+    const long long n_run = tile_end - tile_begin;
+    if (n_run <= 0) return cudaSuccess;
+    const long long big = 1LL << 60;
+    const long long n_tiles_total = last ? tile_end : big;
+    const long long n_out_eff = last ? n_out : big;
+    unsigned int *ticket = s.tickets + 1 + launch_idx;
     const size_t smem = (size_t)tile_bytes + ((size_t)(tile_bytes >> 5) + 8) * 4 +
                         (size_t)(tile_bytes >> 3) + 16;  // tile + group offsets + ready bitmap
 
@@ -493,22 +520,34 @@ cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
         long long grid = (long long)sms * 2;
-        if (grid > n_tiles) grid = n_tiles;
+        if (grid > n_run) grid = n_run;
         kern<<<(unsigned)grid, 768, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
-                                                 s.tile_tok, s.tile_pos, n_tiles, n_out, d_out,
-                                                 s.tile_done, s.tickets, s.info);
+                                                 s.tile_tok, s.tile_pos, tile_begin, tile_end,
+                                                 n_tiles_total, n_out_eff, d_out, s.tile_done,
+                                                 ticket, s.info);
     } else {
         auto kern = lz77_decode_tile_kernel<1024, 1>;
         cudaError_t rc =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
         long long grid = sms;
-        if (grid > n_tiles) grid = n_tiles;
+        if (grid > n_run) grid = n_run;
         kern<<<(unsigned)grid, 1024, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
-                                                  s.tile_tok, s.tile_pos, n_tiles, n_out, d_out,
-                                                  s.tile_done, s.tickets, s.info);
+                                                  s.tile_tok, s.tile_pos, tile_begin, tile_end,
+                                                  n_tiles_total, n_out_eff, d_out, s.tile_done,
+                                                  ticket, s.info);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
+                               long long n_tokens, long long n_out, const Params &P,
+                               void *scratch, uint8_t *d_out, cudaStream_t st)
+{
+    const long long tile_bytes = 1LL << P.block_shift;
+    const long long n_tiles = (n_out + tile_bytes - 1) >> P.block_shift;
+    return launch_decode_tiles_range(d_in_words, n_in_bytes, n_tokens, 0, n_tiles, true, n_out, 0,
+                                     P, scratch, d_out, st);
 }
 
 }  // namespace lz77

@@ -57,6 +57,17 @@ int decode_launch_count(bool with_copy);
 cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, const Params &P, void *scratch,
                                DecodeInfo **d_info, cudaStream_t st);
+// ranged variants for the chunked host path (see decode.cu)
+long long decode_scan_granule();
+cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_bytes,
+                                     long long n_tokens, long long tok_begin, long long tok_end,
+                                     const Params &P, void *scratch, DecodeInfo **d_info,
+                                     cudaStream_t st);
+cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in_bytes,
+                                      long long n_tokens, long long tile_begin,
+                                      long long tile_end, bool last, long long n_out,
+                                      int launch_idx, const Params &P, void *scratch,
+                                      uint8_t *d_out, cudaStream_t st);
 // pass 2: tile decode (needs the decoded size pass 1 produced)
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, long long n_out, const Params &P,

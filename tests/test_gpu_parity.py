@@ -229,3 +229,24 @@ def test_host_chunked_encode_equals_device_encode(lz, orc, sb, la, n):
     assert lz.decode(host_stream) == src.cpu().numpy().tobytes()
     if sb != 1:
         assert orc.decode(host_stream[:4] + host_stream[4:]) == src.cpu().numpy().tobytes()
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (65535, 255), (1000, 20)])
+def test_pipelined_host_paths_small_chunks(lz, orc, sb, la):
+    """With the host chunk set to 1 MiB the chunked encode / decode pipelines run
+    on small inputs: reference-style (unblocked) streams, whose matches reach
+    back across tiles and chunk seams, must still decode bit-exact."""
+    from lz77_b200 import api, synth
+    api.set_host_chunk(1 << 20)
+    try:
+        for kind, n in (("zipf_text", 6_000_001), ("log_like", 5 << 20), ("random", 3 << 20)):
+            data = synth.make(kind, n, seed=41).numpy().tobytes()
+            ref_stream = orc.ref_encode(data, sb, la)
+            assert len(ref_stream) > (2 << 20)
+            assert lz.decode(ref_stream) == data, (kind, "reference-style stream")
+            enc = lz.encode(data, la=la, sb=sb)
+            spec, _ = _spec(orc, lz, data, sb, la)
+            assert enc == spec, (kind, "chunked host encode")
+            assert lz.decode(enc) == data
+    finally:
+        api.set_host_chunk(32 << 20)
