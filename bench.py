@@ -46,6 +46,19 @@ UNIT = "GB/s"
 # helpers
 # --------------------------------------------------------------------------- #
 
+def ncu_traffic(kernel: str, n_bytes: int):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture
+    (profiles/traffic.json), valid only for the workload size it was taken on."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        t = json.loads(p.read_text())
+        if int(t.get("workload_bytes", -1)) == int(n_bytes):
+            return int(t[kernel])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -363,11 +376,14 @@ def run_native(args):
             "clocks": clocks,
             "roofline": {"kernel": "lz77_parse_kernel (longest-match search + greedy parse)",
                          "bound": "hbm", "achieved": search_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": search_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": search_gbs / peak,
+                         "traffic": ncu_traffic("lz77_parse_bucket_kernel", n),
+                         "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes},
             "roofline_decode": {"kernel": "lz77_decode_tile_kernel (match copy)",
                                 "bound": "hbm", "achieved": copy_gbs, "peak": peak,
-                                "unit": "GB/s", "frac": copy_gbs / peak, "traffic": None,
+                                "unit": "GB/s", "frac": copy_gbs / peak,
+                                "traffic": ncu_traffic("lz77_decode_tile_kernel", n),
                                 "algorithmic_bytes": alg_bytes},
         }
         if world == 1 and not args.no_cpu_baseline:
