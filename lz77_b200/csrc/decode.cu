@@ -36,6 +36,7 @@ struct DecodeScratch {
     unsigned long long *status;  // look-back state per scan chunk
     long long *tile_tok;         // token containing the first byte of tile j
     long long *tile_pos;         // output position of that token
+    uint32_t *group_pos;         // low 32 bits of the output position of token 32g
     unsigned int *tile_done;     // tile j has been written to HBM
     unsigned int *tickets;       // [0] scan chunk ticket, [1] tile ticket
     DecodeInfo *info;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(kDsThreads)
 lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
                         Params P, int tile_shift, unsigned long long *status,
                         long long *__restrict__ tile_tok, long long *__restrict__ tile_pos,
-                        unsigned int *tickets, DecodeInfo *info)
+                        uint32_t *__restrict__ group_pos, unsigned int *tickets, DecodeInfo *info)
 {
     __shared__ long long s_chunk;
     __shared__ unsigned long long s_warp_tot[kDsThreads / 32];
@@ -155,6 +156,9 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
         const long long k = warp_base + r * 32 + lane;
         if (k >= n_tokens) continue;
         const long long pos = (long long)(base_pos + incl[r] - L[r]);
+        // low 32 bits of the output position of tokens 32g .. 32g+31 (the tile
+        // kernel only needs positions relative to its tile)
+        if (lane == 0) group_pos[k >> 5] = (uint32_t)pos;
         const long long j = (pos + tile_bytes - 1) >> tile_shift;
         if ((j << tile_shift) < pos + (long long)L[r]) {
             tile_tok[j] = k;
@@ -200,7 +204,8 @@ template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
                         Params P, int tile_shift, const long long *__restrict__ tile_tok,
-                        const long long *__restrict__ tile_pos, long long tile_begin,
+                        const long long *__restrict__ tile_pos,
+                        const uint32_t *__restrict__ group_pos, long long tile_begin,
                         long long tile_end, long long n_tiles, long long n_out, uint8_t *out,
                         unsigned int *tile_done, unsigned int *ticket, DecodeInfo *info)
 {
@@ -208,16 +213,11 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
     constexpr int kWarps = kThreads / 32;
     const int tile_bytes = 1 << tile_shift;
     uint8_t *tile = smem;
-    // gpos[g]: output offset of group g (32 tokens) relative to the tile's first token
-    uint32_t *gpos = reinterpret_cast<uint32_t *>(smem + tile_bytes);
     // one bit per tile byte: the byte holds its final value
-    uint32_t *ready_bits =
-        reinterpret_cast<uint32_t *>(smem + tile_bytes + ((tile_bytes >> 5) + 8) * 4);
+    uint32_t *ready_bits = reinterpret_cast<uint32_t *>(smem + tile_bytes);
 
     __shared__ long long s_tile;
     __shared__ int s_next_group;
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_total;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t off_mask = (1u << P.ob) - 1u;
@@ -238,64 +238,40 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
         if (tile_hi > n_out) tile_hi = n_out;
         const int tile_len = (int)(tile_hi - tile_lo);
         const long long k0 = tile_tok[j];
-        const int p0_rel = (int)(tile_pos[j] - tile_lo);  // <= 0: a token may straddle in
         long long k_end = n_tokens;
         if (j + 1 < n_tiles) k_end = tile_tok[j + 1] + (tile_pos[j + 1] < tile_hi ? 1 : 0);
-        const int n_tok = (int)(k_end - k0);
-        const int n_groups = (n_tok + 31) >> 5;
+        // groups of 32 tokens are global (token 32g .. 32g+31); pass 1 left the output
+        // position of each in group_pos.  The tile's first and last group may hold
+        // tokens of the neighbouring tiles: those lanes only feed the prefix sum.
+        const long long g_first = k0 >> 5;
+        const int n_groups = (int)(((k_end + 31) >> 5) - g_first);
+        const uint32_t tile_lo32 = (uint32_t)tile_lo;
 
-        // ---- phase 1: output offset of every group of 32 tokens -----------
         for (int i = threadIdx.x; i < (tile_bytes >> 5); i += kThreads) ready_bits[i] = 0u;
-        for (int g = warp; g < n_groups; g += kWarps) {
-            const long long k = k0 + g * 32 + lane;
-            uint32_t l1 = 0;
-            if (k < k_end) {
-                const uint32_t tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
-                l1 = ((tok >> P.ob) & len_mask) + 1u;
-            }
-            l1 = __reduce_add_sync(0xffffffffu, l1);
-            if (lane == 0) gpos[g] = l1;
-        }
-        __syncthreads();
-        {
-            const int per = (n_groups + kThreads - 1) / kThreads;
-            const int b = threadIdx.x * per;
-            uint32_t s = 0;
-            for (int i = 0; i < per; i++)
-                if (b + i < n_groups) s += gpos[b + i];
-            uint32_t run = block_exclusive_scan_u32<kThreads>(s, s_warp, &s_total);
-            for (int i = 0; i < per; i++) {
-                if (b + i < n_groups) {
-                    const uint32_t v = gpos[b + i];
-                    gpos[b + i] = run;
-                    run += v;
-                }
-            }
-        }
         __syncthreads();
 
-        // ---- phase 2: one lane per token, groups handed out in order -------
+        // ---- one lane per token, groups handed out in order -----------------
         while (true) {
-            int g = 0;
-            if (lane == 0) g = atomicAdd(&s_next_group, 1);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            if (g >= n_groups) break;
+            int gi = 0;
+            if (lane == 0) gi = atomicAdd(&s_next_group, 1);
+            gi = __shfl_sync(0xffffffffu, gi, 0);
+            if (gi >= n_groups) break;
 
-            const long long k = k0 + g * 32 + lane;
-            const bool valid = k < k_end;
+            const long long k = ((g_first + gi) << 5) + lane;
+            const bool valid = k >= k0 && k < k_end;
             uint32_t tok = 0;
-            if (valid) tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
+            if (k < k_end) tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
             const int off = (int)(tok & off_mask);
             const int len = (int)((tok >> P.ob) & len_mask);
             const uint32_t lit = (tok >> lit_shift) & 0xffu;
-            const int l1 = valid ? len + 1 : 0;
+            const int l1 = k < k_end ? len + 1 : 0;  // lanes before k0 still count in the sum
             int inc = l1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 int t = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += t;
             }
-            const int pos_rel = p0_rel + (int)gpos[g] + inc - l1;
+            const int pos_rel = (int)(__ldg(group_pos + g_first + gi) - tile_lo32) + inc - l1;
             // the part of this token that lies in the tile
             const int d_lo = max(pos_rel, 0), d_hi = min(pos_rel + l1, tile_len);
 
@@ -441,6 +417,8 @@ static DecodeScratch carve_decode(void *scratch, long long n_tokens, const Param
     p += al256((size_t)max_tiles * 8);
     s.tile_pos = (long long *)p;
     p += al256((size_t)max_tiles * 8);
+    s.group_pos = (uint32_t *)p;
+    p += al256((size_t)((n_tokens + 31) / 32) * 4);
     return s;
 }
 
@@ -449,7 +427,7 @@ size_t decode_scratch_bytes(long long n_tokens, const Params &P)
     const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
     const long long max_tiles = ((n_tokens << P.lb) >> P.block_shift) + 2;
     return 512 + al256((size_t)n_chunks * 8) + al256((size_t)max_tiles * 4) +
-           2 * al256((size_t)max_tiles * 8) + 1024;
+           2 * al256((size_t)max_tiles * 8) + al256((size_t)((n_tokens + 31) / 32) * 4) + 1024;
 }
 
 int decode_launch_count(bool with_copy) { return with_copy ? 2 : 1; }
@@ -474,7 +452,7 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
     if (n_chunks > 0)
         lz77_decode_scan_kernel<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(
             d_in_words, n_words, tok_end, P, P.block_shift, s.status, s.tile_tok, s.tile_pos,
-            s.tickets, s.info);
+            s.group_pos, s.tickets, s.info);
     return cudaGetLastError();
 }
 
@@ -508,21 +486,21 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
     const long long n_tiles_total = last ? tile_end : big;
     const long long n_out_eff = last ? n_out : big;
     unsigned int *ticket = s.tickets + 1 + launch_idx;
-    const size_t smem = (size_t)tile_bytes + ((size_t)(tile_bytes >> 5) + 8) * 4 +
-                        (size_t)(tile_bytes >> 3) + 16;  // tile + group offsets + ready bitmap
+    const size_t smem = (size_t)tile_bytes + (size_t)(tile_bytes >> 3) + 16;  // tile + ready bitmap
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (tile_bytes <= 65536) {
-        auto kern = lz77_decode_tile_kernel<768, 2>;
+        auto kern = lz77_decode_tile_kernel<512, 3>;
         cudaError_t rc =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
-        long long grid = (long long)sms * 2;
+        long long grid = (long long)sms * 3;
         if (grid > n_run) grid = n_run;
-        kern<<<(unsigned)grid, 768, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
-                                                 s.tile_tok, s.tile_pos, tile_begin, tile_end,
+        kern<<<(unsigned)grid, 512, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
+                                                 s.tile_tok, s.tile_pos, s.group_pos, tile_begin,
+                                                 tile_end,
                                                  n_tiles_total, n_out_eff, d_out, s.tile_done,
                                                  ticket, s.info);
     } else {
@@ -533,7 +511,8 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
         long long grid = sms;
         if (grid > n_run) grid = n_run;
         kern<<<(unsigned)grid, 1024, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
-                                                  s.tile_tok, s.tile_pos, tile_begin, tile_end,
+                                                  s.tile_tok, s.tile_pos, s.group_pos, tile_begin,
+                                                 tile_end,
                                                   n_tiles_total, n_out_eff, d_out, s.tile_done,
                                                   ticket, s.info);
     }
