@@ -172,6 +172,15 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
 // pass 2: tile decode
 // ---------------------------------------------------------------------------
 
+#ifndef LZ77_DEC_SPINS
+#define LZ77_DEC_SPINS 2
+#endif
+#ifndef LZ77_DEC_SLEEP_NS
+#define LZ77_DEC_SLEEP_NS 40
+#endif
+constexpr int kDecSpins = LZ77_DEC_SPINS;        // polls without progress before backing off
+constexpr unsigned kDecSleepNs = LZ77_DEC_SLEEP_NS;
+
 // ready bitmap: bit i of the tile is set once byte i holds its final value
 __device__ __forceinline__ void ready_mark(uint32_t *bits, int a, int b)  // [a, b), a < b
 {
@@ -364,8 +373,8 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                     __syncwarp();
                     prev_rm = 0;
                     spins = 0;
-                } else if (rm == 0u && ++spins > 2) {
-                    __nanosleep(40);  // leave the issue slots to the warps we wait for
+                } else if (rm == 0u && ++spins > kDecSpins) {
+                    __nanosleep(kDecSleepNs);  // leave the issue slots to the warps we wait for
                 }
             }
         }
