@@ -65,6 +65,110 @@ __device__ __forceinline__ int group_lower_bound(const PosT *e, int n, int lo, i
     return base + (m ? __ffs(m) - 1 : kLanes);  // lanes beyond cnt report true, so <= base + cnt
 }
 
+
+// ---- shared-memory reads by 32-bit shared address --------------------------
+// Inside the token loop every read goes through an explicit shared-window
+// address computed once per kernel: with generic pointers the compiler
+// re-derives the CTA's shared window base (S2R SR_CgaCtaId + LEA) in front of
+// every access sequence.
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// match_len() of match.cuh on shared addresses (sdata = shared address of the
+// staged bytes)
+template <bool kSmallLA>
+__device__ __forceinline__ int match_len_s(uint32_t sdata, int q, int p0,
+                                           const uint32_t (&tgt)[4], int max_len)
+{
+    const uint32_t w = sdata + (uint32_t)(q & ~3);
+    const int sh = (q & 3) * 8;
+    if (kSmallLA) {
+        const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
+        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+        int l;
+        if (x) {
+            l = (__ffs(x) - 1) >> 3;
+        } else {
+            const uint32_t a2 = lds32(w + 8);
+            x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+            if (x) {
+                l = 4 + ((__ffs(x) - 1) >> 3);
+            } else {
+                const uint32_t a3 = lds32(w + 12);
+                x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+                if (x) {
+                    l = 8 + ((__ffs(x) - 1) >> 3);
+                } else {
+                    const uint32_t a4 = lds32(w + 16);
+                    x = __funnelshift_r(a3, a4, sh) ^ tgt[3];
+                    l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
+                }
+            }
+        }
+        return min(l, max_len);
+    } else {
+        int l = 0;
+        uint32_t a = lds32(w);
+        uint32_t wa = w + 4;
+        while (l < max_len) {
+            const uint32_t b = lds32(wa);
+            wa += 4;
+            const int pi = p0 + l;
+            const uint32_t pw = sdata + (uint32_t)(pi & ~3);
+            const uint32_t t = __funnelshift_r(lds32(pw), lds32(pw + 4), (pi & 3) * 8);
+            const uint32_t x = __funnelshift_r(a, b, sh) ^ t;
+            if (x) {
+                l += (__ffs(x) - 1) >> 3;
+                break;
+            }
+            l += 4;
+            a = b;
+        }
+        return min(l, max_len);
+    }
+}
+
+// first index in [0, n) of the ascending uint16 list at shared address se whose
+// value is >= lo (n if none); uniform across the kLanes lanes of a group
+template <int kLanes>
+__device__ __forceinline__ int group_lower_bound_s(uint32_t se, int n, int lo, int sl,
+                                                   unsigned gmask, int gshift)
+{
+    int base = 0, cnt = n;
+    while (cnt > kLanes) {
+        const int step = (cnt + kLanes - 1) / kLanes;
+        const int idx = base + sl * step;
+        const bool ge = idx < base + cnt ? (int)lds16(se + 2u * idx) >= lo : true;
+        const unsigned m = __ballot_sync(gmask, ge) >> gshift;
+        const int first = m ? __ffs(m) - 1 : kLanes;
+        if (first == 0) return base;
+        const int nb = base + (first - 1) * step + 1;
+        const int ne = min(base + cnt, base + first * step + 1);
+        base = nb;
+        cnt = ne - nb;
+    }
+    const int idx = base + sl;
+    const bool ge = idx < base + cnt ? (int)lds16(se + 2u * idx) >= lo : true;
+    const unsigned m = __ballot_sync(gmask, ge) >> gshift;
+    return base + (m ? __ffs(m) - 1 : kLanes);
+}
+
 // kLanes lanes (a "group": 32, 16 or 8) cooperate on one parse segment, so a warp
 // parses 32 / kLanes segments side by side: the per-token scalar work (target
 // load, bucket lookup, window bound, reduction, emit) is issued once for all
@@ -96,6 +200,10 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int cnt_col = warp >> 1, cnt_sh = (warp & 1) * 16;
+    static_assert(!kSortedGlobal && sizeof(PosT) == 2, "the token loop reads uint16 buckets from shared memory");
+    const uint32_t sdata = smem_u32(smem);       // shared-window addresses, computed once
+    const uint32_t sbstart = smem_u32(bstart);
+    const uint32_t ssorted = smem_u32(sorted);
     const int sg = lane / kLanes, sl = lane % kLanes;  // group in the warp, lane in the group
     const int gshift = sg * kLanes;
     const unsigned gmask = kLanes == 32 ? 0xffffffffu : ((1u << (kLanes & 31)) - 1u) << gshift;
@@ -216,12 +324,12 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     // lookahead: 16 bytes at p0 from five aligned words
                     uint32_t tgt[4];
                     {
-                        const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (p0 & ~3));
+                        const uint32_t w = sdata + (uint32_t)(p0 & ~3);
                         const int sh = (p0 & 3) * 8;
-                        const uint32_t a0 = w[0], a1 = w[1];
+                        const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
                         tgt[0] = __funnelshift_r(a0, a1, sh);
                         if (kSmallLA) {
-                            const uint32_t a2 = w[2], a3 = w[3], a4 = w[4];
+                            const uint32_t a2 = lds32(w + 8), a3 = lds32(w + 12), a4 = lds32(w + 16);
                             tgt[1] = __funnelshift_r(a1, a2, sh);
                             tgt[2] = __funnelshift_r(a2, a3, sh);
                             tgt[3] = __funnelshift_r(a3, a4, sh);
@@ -231,22 +339,22 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     }
                     const int key = (int)((tgt[0] & 0xffu) << kKeyLow) |
                                     (int)((tgt[0] >> 8) & ((1u << kKeyLow) - 1u));
-                    const int bs = (int)bstart[key];
-                    const int bn = (int)bstart[key + 1] - bs;
-                    const PosT *e = sorted + bs;
+                    const int bs = (int)lds16(sbstart + 2u * key);
+                    const int bn = (int)lds16(sbstart + 2u * key + 2u) - bs;
+                    const uint32_t se = ssorted + 2u * bs;  // shared address of the bucket
                     int best_len = 0, best_q = 0;
                     // candidates: bucket entries in [lo_idx, p0), oldest first; short
                     // buckets are walked from their start, long ones from the window's
                     // lower bound
                     int i = bn <= kLinearScan
                                 ? 0
-                                : group_lower_bound<kLanes>(e, bn, lo_idx, sl, gmask, gshift);
+                                : group_lower_bound_s<kLanes>(se, bn, lo_idx, sl, gmask, gshift);
                     for (; i < bn; i += kLanes) {
                         const int idx = i + sl;
-                        const int q = idx < bn ? (int)e[idx] : 0x7fffffff;
+                        const int q = idx < bn ? (int)lds16(se + 2u * idx) : 0x7fffffff;
                         if (q >= lo_idx && q < p0) {
                             // nearer than anything this lane has seen: must be longer
-                            const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
+                            const int l = match_len_s<kSmallLA>(sdata, q, p0, tgt, max_len);
                             if (l > best_len) {
                                 best_len = l;
                                 best_q = q;
@@ -261,19 +369,22 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     int q_best = (int)(0xfffffu - (k & 0xfffffu));
                     if (len < 2) {
                         // length 1: the oldest in-window position with the same first
-                        // byte, in any of the 8 buckets of that byte
+                        // byte, in any of the buckets of that byte
                         int q1 = 0x7fffffff;
                         if (sl < (1 << kKeyLow)) {
                             const int kb = (key & ~((1 << kKeyLow) - 1)) + sl;
-                            const int s1 = (int)bstart[kb];
-                            int lo_i = 0, hi_i = (int)bstart[kb + 1] - s1;
-                            const PosT *e1 = sorted + s1;
+                            const int s1 = (int)lds16(sbstart + 2u * kb);
+                            int lo_i = 0, hi_i = (int)lds16(sbstart + 2u * kb + 2u) - s1;
+                            const uint32_t se1 = ssorted + 2u * s1;
                             const int n1 = hi_i;
                             while (lo_i < hi_i) {  // lower bound of lo_idx
                                 const int mid = (lo_i + hi_i) >> 1;
-                                if ((int)e1[mid] < lo_idx) lo_i = mid + 1; else hi_i = mid;
+                                if ((int)lds16(se1 + 2u * mid) < lo_idx) lo_i = mid + 1; else hi_i = mid;
                             }
-                            if (lo_i < n1 && (int)e1[lo_i] < p0) q1 = (int)e1[lo_i];
+                            if (lo_i < n1) {
+                                const int qq = (int)lds16(se1 + 2u * lo_i);
+                                if (qq < p0) q1 = qq;
+                            }
                         }
                         q1 = (int)__reduce_min_sync(gmask, (unsigned)q1);
                         len = q1 != 0x7fffffff ? 1 : 0;
@@ -282,7 +393,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     off = len ? p0 - q_best : 0;
                 }
 
-                const uint32_t lit = smem[p0 + len];
+                const uint32_t lit = lds8(sdata + (uint32_t)(p0 + len));
                 const uint32_t tok =
                     (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
                 if (sl == (ntok & (kLanes - 1))) held = tok;
