@@ -342,6 +342,7 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                 prev_rm = rm;
                 if (go) {
                     if (ready) {  // ascending byte copy, lz77.c:178-188
+                        __threadfence_block();  // acquire: bitmap read -> source bytes
                         if (fast) {
                             const volatile uint8_t *src = tile + s_rel;
                             uint8_t *dst = tile + pos_rel;
