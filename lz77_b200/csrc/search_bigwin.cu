@@ -7,8 +7,8 @@
 //
 //   lz77_block_sort_kernel   one CTA per block.  The block is staged into shared
 //       memory with one TMA bulk copy, then its positions are sorted by
-//       key = x[q] << 5 | x[q+1] & 31 (8192 buckets) with a stable two-pass LSD
-//       radix sort (digit x[q+1]&31, then digit x[q]); per-warp digit counters
+//       key = (x[q] & 127) << 6 | x[q+1] & 63 (8192 buckets) with a stable two-pass
+//       LSD radix sort (digit x[q+1]&63, then digit x[q]&127); per-warp digit counters
 //       + MATCH.ANY ranks keep every bucket in ascending position order.
 //       Output: sorted positions (uint32) and 8193 bucket starts per block.
 //   lz77_parse_bigwin_kernel one CTA (16 warps) per 16 KiB tile: TMA-stages up to
@@ -26,8 +26,16 @@
 
 namespace lz77 {
 
-constexpr int kBigKeyLow = 5;
-constexpr int kBigBuckets = 256 << kBigKeyLow;  // 8192
+// key = low 7 bits of x[q], low 6 bits of x[q+1]: a perfect hash of the byte pair
+// for ASCII text, an even spread for binary data
+constexpr int kBigB0Bits = 7, kBigB1Bits = 6;
+constexpr int kBigBuckets = 1 << (kBigB0Bits + kBigB1Bits);  // 8192
+
+__device__ __forceinline__ int big_key(uint32_t b0, uint32_t b1)
+{
+    return (int)(((b0 & ((1u << kBigB0Bits) - 1u)) << kBigB1Bits) |
+                 (b1 & ((1u << kBigB1Bits) - 1u)));
+}
 constexpr int kSortThreads = 1024;
 constexpr int kSortWarps = kSortThreads / 32;
 
@@ -128,13 +136,12 @@ lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_sh
 
     // bucket sizes (for the bucket start table)
     for (int i = threadIdx.x; i < nb; i += kSortThreads)
-        atomicAdd(&cnt2[((int)data[i] << kBigKeyLow) | (data[i + 1] & ((1 << kBigKeyLow) - 1))],
-                  1u);
+        atomicAdd(&cnt2[big_key(data[i], data[i + 1])], 1u);
     // pass 1: low digit = x[q+1] & 31 ; pass 2: high digit = x[q]
-    radix_pass<1 << kBigKeyLow>(nullptr, my_tmp, nb, cnt, bin_start, s_warp, &s_total,
-                                [&](uint32_t q) { return (int)(data[q + 1] & ((1 << kBigKeyLow) - 1)); });
-    radix_pass<256>(my_tmp, my_sorted, nb, cnt, bin_start, s_warp, &s_total,
-                    [&](uint32_t q) { return (int)data[q]; });
+    radix_pass<1 << kBigB1Bits>(nullptr, my_tmp, nb, cnt, bin_start, s_warp, &s_total,
+                                [&](uint32_t q) { return (int)(data[q + 1] & ((1u << kBigB1Bits) - 1u)); });
+    radix_pass<1 << kBigB0Bits>(my_tmp, my_sorted, nb, cnt, bin_start, s_warp, &s_total,
+                                [&](uint32_t q) { return (int)(data[q] & ((1u << kBigB0Bits) - 1u)); });
     // bucket starts: exclusive scan of the 8192 bucket sizes
     {
         constexpr int per = kBigBuckets / kSortThreads;  // 8
@@ -264,8 +271,7 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             const uint32_t b0 = tgt[0] & 0xffu;
             int best_len = 0, best_q = 0;
             if (max_len >= 2) {
-                const int key = (int)(b0 << kBigKeyLow) |
-                                (int)((tgt[0] >> 8) & ((1u << kBigKeyLow) - 1u));
+                const int key = big_key(b0, tgt[0] >> 8);
                 const int bs = (int)__ldg(blk_bstart + key);
                 const int bn = (int)__ldg(blk_bstart + key + 1) - bs;
                 const uint32_t *e = blk_sorted + bs;

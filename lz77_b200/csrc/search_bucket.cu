@@ -8,7 +8,7 @@
 // bytes, then a token only verifies the positions that share its key.
 //
 //   build (per tile, all warps)
-//     key(q) = x[q] << 2 | x[q+1] & 3                     (1024 buckets)
+//     key(q) = (x[q] & 31) << 5 | x[q+1] & 31             (1024 buckets)
 //     stable counting sort of the tile's positions by key: per-warp histogram
 //     of a contiguous chunk (packed 16-bit counters, shared-memory atomics),
 //     column scan across warps + bucket scan, then an in-order scatter whose
@@ -19,24 +19,32 @@
 //     -> 32 candidates per round, oldest first, verified against the target
 //     held in registers -> (length, oldest start) reduced with REDUX; stops at
 //     the first maximum-length match.
-//     A match of length 1 can sit in any of the 4 buckets that share the first
-//     byte; when nothing longer exists, 4 lanes binary-search those buckets for
-//     the oldest in-window position.
+//     A match of length 1 can sit in many buckets; when nothing longer exists the
+//     warp scans the staged window forward (SWAR byte compare, 512 bytes per
+//     step) for the oldest occurrence of the first byte.
 #include "kernels.cuh"
 #include "match.cuh"
 
 namespace lz77 {
 
-#ifndef LZ77_KEY_LOW_BITS
-#define LZ77_KEY_LOW_BITS 2
+// Bucket key: the low kKeyBits bits of each of the two bytes.  For lowercase text
+// this is a perfect hash of the byte pair (one bucket per digram); for binary
+// data it spreads the 65536 pairs evenly.
+#ifndef LZ77_KEY_BITS
+#define LZ77_KEY_BITS 5
 #endif
-constexpr int kKeyLow = LZ77_KEY_LOW_BITS;        // bits of the second byte in the key
-constexpr int kBuckets = 256 << kKeyLow;
+constexpr int kKeyBits = LZ77_KEY_BITS;
+constexpr int kBuckets = 1 << (2 * kKeyBits);
 constexpr int kLinearScan = 128;  // buckets up to this size are scanned from their start
+
+__device__ __forceinline__ int pair_key(uint32_t b0, uint32_t b1)
+{
+    return (int)(((b0 & ((1u << kKeyBits) - 1u)) << kKeyBits) | (b1 & ((1u << kKeyBits) - 1u)));
+}
 
 __device__ __forceinline__ int bucket_key(const uint8_t *smem, int i)
 {
-    return ((int)smem[i] << kKeyLow) | ((int)smem[i + 1] & ((1 << kKeyLow) - 1));
+    return pair_key(smem[i], smem[i + 1]);
 }
 
 // first index in [0, n) of the ascending list e[] whose value is >= lo (n if none);
@@ -337,8 +345,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                             tgt[1] = tgt[2] = tgt[3] = 0;
                         }
                     }
-                    const int key = (int)((tgt[0] & 0xffu) << kKeyLow) |
-                                    (int)((tgt[0] >> 8) & ((1u << kKeyLow) - 1u));
+                    const int key = pair_key(tgt[0], tgt[0] >> 8);
                     const int bs = (int)lds16(sbstart + 2u * key);
                     const int bn = (int)lds16(sbstart + 2u * key + 2u) - bs;
                     const uint32_t se = ssorted + 2u * bs;  // shared address of the bucket
@@ -368,23 +375,31 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     len = (int)(k >> 20);
                     int q_best = (int)(0xfffffu - (k & 0xfffffu));
                     if (len < 2) {
-                        // length 1: the oldest in-window position with the same first
-                        // byte, in any of the buckets of that byte
+                        // length 1: the oldest byte of the window equal to the first
+                        // lookahead byte -- forward SWAR scan of the staged window, 512
+                        // bytes per step (such bytes sit in many buckets)
+                        const uint32_t b0x4 = (tgt[0] & 0xffu) * 0x01010101u;
                         int q1 = 0x7fffffff;
-                        if (sl < (1 << kKeyLow)) {
-                            const int kb = (key & ~((1 << kKeyLow) - 1)) + sl;
-                            const int s1 = (int)lds16(sbstart + 2u * kb);
-                            int lo_i = 0, hi_i = (int)lds16(sbstart + 2u * kb + 2u) - s1;
-                            const uint32_t se1 = ssorted + 2u * s1;
-                            const int n1 = hi_i;
-                            while (lo_i < hi_i) {  // lower bound of lo_idx
-                                const int mid = (lo_i + hi_i) >> 1;
-                                if ((int)lds16(se1 + 2u * mid) < lo_idx) lo_i = mid + 1; else hi_i = mid;
+                        for (int base = lo_idx & ~15; base < p0; base += kLanes * 16) {
+                            const int g = base + sl * 16;
+                            if (g < p0) {
+                                const uint32_t ga = sdata + (uint32_t)g;
+                                uint32_t wv[4];
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3])
+                                             : "r"(ga));
+#pragma unroll
+                                for (int wi = 3; wi >= 0; wi--) {
+                                    uint32_t m = zero_bytes(wv[wi] ^ b0x4);
+                                    while (m) {
+                                        const int bit = __ffs(m) - 1;
+                                        m ^= 1u << bit;
+                                        const int q = g + 4 * wi + (bit >> 3);
+                                        if (q >= lo_idx && q < p0 && q < q1) q1 = q;
+                                    }
+                                }
                             }
-                            if (lo_i < n1) {
-                                const int qq = (int)lds16(se1 + 2u * lo_i);
-                                if (qq < p0) q1 = qq;
-                            }
+                            if (__any_sync(gmask, q1 != 0x7fffffff)) break;
                         }
                         q1 = (int)__reduce_min_sync(gmask, (unsigned)q1);
                         len = q1 != 0x7fffffff ? 1 : 0;
