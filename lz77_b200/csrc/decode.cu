@@ -10,8 +10,8 @@
 //           token that contains its first byte.
 //   pass 2  lz77_decode_tile_kernel   one CTA per output tile: the tile is
 //           assembled in shared memory with one lane per token (literal store +
-//           ascending match copy, lz77.c:178-194) and written to HBM with
-//           128-bit stores.  Match sources inside the tile are read from shared
+//           ascending match copy, lz77.c:178-194) and written to HBM with one
+//           TMA bulk store.  Match sources inside the tile are read from shared
 //           memory behind an in-order commit frontier; sources in earlier tiles
 //           (streams the reference encoder wrote reach back SB bytes from
 //           anywhere) are read from HBM once that tile has been published.
@@ -381,12 +381,16 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
         }
         __syncthreads();
 
-        // ---- flush the tile with 128-bit stores -----------------------------
+        // ---- flush the tile: one TMA bulk store (shared -> global) -----------
         {
             uint8_t *dst = out + tile_lo;
             const int n16 = tile_len & ~15;
-            for (int i = threadIdx.x * 16; i < n16; i += kThreads * 16)
-                *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(tile + i);
+            fence_proxy_async();  // the tile was written through the generic proxy
+            __syncthreads();
+            if (threadIdx.x == 0 && n16 > 0) {
+                tma_store_1d(dst, tile, (uint32_t)n16);
+                tma_store_commit_wait();  // complete (and visible) before the flag below
+            }
             for (int i = n16 + threadIdx.x; i < tile_len; i += kThreads) dst[i] = tile[i];
         }
         __threadfence();

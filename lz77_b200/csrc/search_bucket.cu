@@ -47,33 +47,6 @@ __device__ __forceinline__ int bucket_key(const uint8_t *smem, int i)
     return pair_key(smem[i], smem[i + 1]);
 }
 
-// first index in [0, n) of the ascending list e[] whose value is >= lo (n if none);
-// uniform across the kLanes lanes of a group, kLanes probes per step
-template <int kLanes, typename PosT>
-__device__ __forceinline__ int group_lower_bound(const PosT *e, int n, int lo, int sl,
-                                                 unsigned gmask, int gshift)
-{
-    int base = 0, cnt = n;
-    while (cnt > kLanes) {
-        const int step = (cnt + kLanes - 1) / kLanes;
-        const int idx = base + sl * step;
-        const bool ge = idx < base + cnt ? (int)e[idx] >= lo : true;
-        const unsigned m = __ballot_sync(gmask, ge) >> gshift;
-        const int first = m ? __ffs(m) - 1 : kLanes;
-        if (first == 0) return base;
-        // the answer lies in (probe[first-1], probe[first]]
-        const int nb = base + (first - 1) * step + 1;
-        const int ne = min(base + cnt, base + first * step + 1);
-        base = nb;
-        cnt = ne - nb;
-    }
-    const int idx = base + sl;
-    const bool ge = idx < base + cnt ? (int)e[idx] >= lo : true;
-    const unsigned m = __ballot_sync(gmask, ge) >> gshift;
-    return base + (m ? __ffs(m) - 1 : kLanes);  // lanes beyond cnt report true, so <= base + cnt
-}
-
-
 // ---- shared-memory reads by 32-bit shared address --------------------------
 // Inside the token loop every read goes through an explicit shared-window
 // address computed once per kernel: with generic pointers the compiler
