@@ -6,13 +6,15 @@
 // no serial bitstream parse.
 //
 //   pass 1  lz77_decode_scan_kernel   one pass over the tokens (decoupled
-//           look-back prefix sum): decoded size, and for every output tile the
-//           token that contains its first byte.
+//           look-back prefix sum): decoded size, for every output tile the
+//           token that contains its first byte, and the output position of
+//           every group of 32 tokens.
 //   pass 2  lz77_decode_tile_kernel   one CTA per output tile: the tile is
 //           assembled in shared memory with one lane per token (literal store +
 //           ascending match copy, lz77.c:178-194) and written to HBM with one
-//           TMA bulk store.  Match sources inside the tile are read from shared
-//           memory behind an in-order commit frontier; sources in earlier tiles
+//           TMA bulk store.  A match is copied as soon as a per-byte "ready"
+//           bitmap shows its source bytes final (dataflow execution: no commit
+//           order, no barrier between tokens); sources in earlier tiles
 //           (streams the reference encoder wrote reach back SB bytes from
 //           anywhere) are read from HBM once that tile has been published.
 //           Streams of the block-parallel encoder never leave their tile

@@ -2,13 +2,14 @@
 //
 // Replaces, for a batch of independent blocks at once:
 //   tree.c:62-260 (BST insert/find/delete/updateOffset)  -> shared-memory
-//       windowed warp search (lz77_parse_kernel)
+//       windowed warp search: bucketed in search_bucket.cu / search_bigwin.cu
+//       (the default), exhaustive in lz77_parse_kernel below (cross-check)
 //   lz77.c:89-135 (greedy token loop, match() lz77.c:209-224) -> one warp per
 //       parse segment, sequential in the segment, parallel across segments
 //   lz77.c:246-252 writecode + bitio.c:203-239 bitIO_write -> warp-cooperative
 //       bit-packer (lz77_pack_kernel)
 //
-// The result is the stream oracle/lz77_oracle.c:lz77o_blocked_encode() defines,
+// The result is the stream oracle/lz77_oracle.c:lz77o_segmented_encode() defines,
 // byte for byte: inside a block the longest match (<= min(LA, bytes left in the
 // segment) - 1) against the last min(window, position in block) bytes, farthest
 // offset among the longest (keeps the decoder's dependency chains short), then
@@ -19,7 +20,8 @@
 namespace lz77 {
 
 // ---------------------------------------------------------------------------
-// K1: longest-match search + greedy parse
+// K1 (first generation, kept as a cross-check: -DLZ77_EXHAUSTIVE_SCAN=1 routes
+// large windows here): exhaustive longest-match search + greedy parse
 // ---------------------------------------------------------------------------
 //
 // One CTA stages `hist` history bytes + nwarps*kSegBytes input bytes into
