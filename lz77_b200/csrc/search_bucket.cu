@@ -154,8 +154,11 @@ __device__ __forceinline__ int group_lower_bound_s(uint32_t se, int n, int lo, i
 // parses 32 / kLanes segments side by side: the per-token scalar work (target
 // load, bucket lookup, window bound, reduction, emit) is issued once for all
 // the groups of a warp that are in step.
+#ifndef LZ77_PARSE_MINBLOCKS
+#define LZ77_PARSE_MINBLOCKS 1
+#endif
 template <bool kSmallLA, int kWarps, int kLanes, typename PosT, bool kSortedGlobal>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, LZ77_PARSE_MINBLOCKS)
 lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
                          long long n_tiles, uint32_t *__restrict__ tok_tmp,
                          uint32_t *__restrict__ seg_ntok, PosT *sorted_global,
