@@ -35,7 +35,10 @@ namespace lz77 {
 #endif
 constexpr int kKeyBits = LZ77_KEY_BITS;
 constexpr int kBuckets = 1 << (2 * kKeyBits);
-constexpr int kLinearScan = 128;  // buckets up to this size are scanned from their start
+#ifndef LZ77_LINEAR_SCAN
+#define LZ77_LINEAR_SCAN 128
+#endif
+constexpr int kLinearScan = LZ77_LINEAR_SCAN;  // buckets up to this size are scanned from their start
 
 __device__ __forceinline__ int pair_key(uint32_t b0, uint32_t b1)
 {
