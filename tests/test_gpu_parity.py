@@ -296,3 +296,41 @@ def test_fuzz_parameters(lz, orc, kind, sb, la, n, seed):
             ref_ok = False
         if ref_ok:
             assert lz.decode(ref_stream) == data
+
+
+def test_c_abi_error_codes(lz):
+    """Error behaviour of the entry points: bad arguments, short output buffers
+    and malformed streams are reported, never fatal."""
+    import ctypes as C
+    from lz77_b200 import api
+    lib = api.load_library()
+    data = np.frombuffer(b"abcabcabcabcX" * 1000, dtype=np.uint8).copy()
+    out = np.zeros(api.encode_bound(data.size) + 16, dtype=np.uint8)
+    n = C.c_long(0)
+    assert lib.lz77_gpu_encode(data.ctypes.data, data.size, -1, -1, out.ctypes.data, out.size,
+                               C.byref(n)) == 0
+    stream = out[:n.value].copy()
+    # output buffer too small
+    small = np.zeros(16, dtype=np.uint8)
+    assert lib.lz77_gpu_encode(data.ctypes.data, data.size, -1, -1, small.ctypes.data, 16,
+                               C.byref(n)) == api.E_SPACE
+    assert lib.lz77_gpu_decode(stream.ctypes.data, stream.size, small.ctypes.data, 16,
+                               C.byref(n)) == api.E_SPACE
+    assert n.value == data.size          # the required size is still reported
+    # bad parameters
+    for sb, la in ((0, 15), (65536, 15), (4095, 0), (4095, 256), (-2, 15)):
+        assert lib.lz77_gpu_encode(data.ctypes.data, data.size, sb, la, out.ctypes.data, out.size,
+                                   C.byref(n)) == api.E_ARG
+    assert lib.lz77_gpu_encode(None, 10, -1, -1, out.ctypes.data, out.size, C.byref(n)) == api.E_ARG
+    assert lib.lz77_gpu_encode(data.ctypes.data, -1, -1, -1, out.ctypes.data, out.size,
+                               C.byref(n)) == api.E_ARG
+    # malformed streams
+    assert lib.lz77_gpu_decode_size(stream.ctypes.data, 3, C.byref(n)) == api.E_STREAM
+    bad = stream.copy()
+    bad[4:7] = (0xff, 0x1f, 0x41)        # first token: offset 4095, length 1 -> before the start
+    back = np.zeros(data.size + 16, dtype=np.uint8)
+    assert lib.lz77_gpu_decode(bad.ctypes.data, bad.size, back.ctypes.data, back.size,
+                               C.byref(n)) == api.E_STREAM
+    # the library still works afterwards
+    assert lz.decode(stream.tobytes()) == data.tobytes()
+    assert lib.lz77_gpu_strerror(api.E_STREAM).decode() == "malformed stream"
