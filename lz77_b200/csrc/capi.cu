@@ -25,7 +25,8 @@ struct Context {
     cudaStream_t own_stream = nullptr;  // created by init; used unless the caller sets one
     cudaStream_t copy_in = nullptr;     // H2D / D2H streams of the chunked host path
     cudaStream_t copy_out = nullptr;
-    cudaStream_t aux = nullptr;         // second compute stream (chunked decode)
+    cudaStream_t aux = nullptr;         // extra compute streams of the chunked host paths
+    cudaStream_t aux2 = nullptr;
     unsigned long long *pinned_totals = nullptr;  // running token count per host chunk
     void *scratch = nullptr;
     size_t scratch_cap = 0;
@@ -42,7 +43,7 @@ struct Context {
 
 Context g;
 
-long long kHostChunkBytes = 32ll << 20;  // host entry points pipeline in chunks of this size
+long long kHostChunkBytes = 16ll << 20;  // host entry points pipeline in chunks of this size
 constexpr long long kMaxHostChunks = 4096;
 
 int fail_cuda(cudaError_t rc, const char *what)
@@ -154,6 +155,7 @@ void lz77_gpu_shutdown(void)
     if (g.copy_in) cudaStreamDestroy(g.copy_in);
     if (g.copy_out) cudaStreamDestroy(g.copy_out);
     if (g.aux) cudaStreamDestroy(g.aux);
+    if (g.aux2) cudaStreamDestroy(g.aux2);
     cudaStreamDestroy(g.own_stream);
     g = Context();
 }
@@ -176,6 +178,7 @@ int lz77_gpu_init(int device)
     CK(cudaStreamCreateWithFlags(&g.copy_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_out, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.aux, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.aux2, cudaStreamNonBlocking));
     CK(cudaMallocHost((void **)&g.pinned_totals, kMaxHostChunks * sizeof(unsigned long long)));
     g.device = device;
     g.ready = true;
@@ -219,7 +222,7 @@ void lz77_gpu_set_timing(int enabled) { g.timing = enabled != 0; }
 
 void lz77_gpu_set_host_chunk(long bytes)
 {
-    // <= 0: no chunking (one H2D, the kernels, one D2H); the default is 32 MiB
+    // <= 0: no chunking (one H2D, the kernels, one D2H); the default is 16 MiB
     kHostChunkBytes = bytes > 0 ? bytes : (1ll << 62);
 }
 
@@ -303,24 +306,43 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in, P));
         if (rc) return rc;
         const EncodePlan pl = encode_plan(g.scratch, n_in, P);
-        std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks);
+        std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks), ev_parse(n_chunks);
         for (long long c = 0; c < n_chunks; c++) {
             CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ev_parse[c], cudaEventDisableTiming));
         }
+        // (the large-window search keeps its bucket tables in one scratch area, so its
+        // chunks must not overlap)
+        const bool split_search = P.window <= 8191;
         // the copy streams start after whatever the compute stream still has queued
         CK(cudaEventRecord(g.ev[4], g.stream));
         CK(cudaStreamWaitEvent(g.copy_in, g.ev[4], 0));
         CK(cudaStreamWaitEvent(g.copy_out, g.ev[4], 0));
+        CK(cudaStreamWaitEvent(g.aux, g.ev[4], 0));
+        CK(cudaStreamWaitEvent(g.aux2, g.ev[4], 0));
         for (long long c = 0; c < n_chunks; c++) {
             const long long lo = c * chunk;
             const long long len = (lo + chunk <= n_in) ? chunk : n_in - lo;
             CK(cudaMemcpyAsync((char *)g.stage_in + lo, in + lo, (size_t)len,
                                cudaMemcpyHostToDevice, g.copy_in));
             CK(cudaEventRecord(ev_in[c], g.copy_in));
-            CK(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
-            CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
-                                   (uint32_t *)g.stage_out, g.stream, nullptr));
+            if (split_search) {
+                // searches of consecutive chunks alternate between two streams so the
+                // tail of one overlaps the head of the next; scan + pack follow in order
+                cudaStream_t ps = (c & 1) ? g.aux2 : g.aux;
+                CK(cudaStreamWaitEvent(ps, ev_in[c], 0));
+                CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
+                                       (uint32_t *)g.stage_out, ps, nullptr, 1));
+                CK(cudaEventRecord(ev_parse[c], ps));
+                CK(cudaStreamWaitEvent(g.stream, ev_parse[c], 0));
+                CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
+                                       (uint32_t *)g.stage_out, g.stream, nullptr, 2));
+            } else {
+                CK(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
+                CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
+                                       (uint32_t *)g.stage_out, g.stream, nullptr, 0));
+            }
             CK(cudaMemcpyAsync(&g.pinned_totals[c], pl.total, 8, cudaMemcpyDeviceToHost,
                                g.stream));
             CK(cudaEventRecord(ev_done[c], g.stream));
@@ -348,9 +370,12 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         }
         CK(cudaStreamSynchronize(g.copy_out));
         CK(cudaStreamSynchronize(g.stream));
+        CK(cudaStreamSynchronize(g.aux));
+        CK(cudaStreamSynchronize(g.aux2));
         for (long long c = 0; c < n_chunks; c++) {
             cudaEventDestroy(ev_in[c]);
             cudaEventDestroy(ev_done[c]);
+            cudaEventDestroy(ev_parse[c]);
         }
         if (result != LZ77_OK) return result;
         *n_out = done_bytes;
@@ -445,7 +470,7 @@ constexpr long long kMaxDecodeChunks = 48;  // one ticket slot per tile launch (
 // them all run concurrently (copy_in / compute / aux / copy_out streams).  The
 // stage_in buffer has already been sized by the caller.
 int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, long out_cap,
-                     long *n_out, long long n_chunks)
+                     long *n_out, long long chunk_bytes, long long n_chunks)
 {
     Params P;
     long long K = 0;
@@ -484,8 +509,8 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
     DecodeInfo *d_info = nullptr;
     long long tok_lo = 0;
     for (long long c = 0; c < n_chunks; c++) {
-        const long long lo = c * kHostChunkBytes;
-        const long long hi = (c + 1 == n_chunks) ? n_in : lo + kHostChunkBytes;
+        const long long lo = c * chunk_bytes;
+        const long long hi = (c + 1 == n_chunks) ? n_in : lo + chunk_bytes;
         CK(cudaMemcpyAsync((char *)g.stage_in + lo, in + lo, (size_t)(hi - lo),
                            cudaMemcpyHostToDevice, g.copy_in));
         CK(cudaEventRecord(ev_in[c], g.copy_in));
@@ -615,10 +640,14 @@ int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long
     int rc = grow(&g.stage_in, &g.stage_in_cap, in_cap + 16);
     if (rc) return rc;
     {
-        // large streams: chunked pipeline (see decode_pipelined)
-        const long long n_chunks = (n_in + kHostChunkBytes - 1) / kHostChunkBytes;
+        // large streams: chunked pipeline (see decode_pipelined); very large ones use
+        // bigger chunks so that the number of tile launches stays bounded
+        long long chunk_bytes = kHostChunkBytes;
+        if ((n_in + chunk_bytes - 1) / chunk_bytes > kMaxDecodeChunks)
+            chunk_bytes = ((n_in + kMaxDecodeChunks - 1) / kMaxDecodeChunks + 0xfffff) & ~0xfffffLL;
+        const long long n_chunks = (n_in + chunk_bytes - 1) / chunk_bytes;
         if (n_chunks >= 2 && n_chunks <= kMaxDecodeChunks && out)
-            return decode_pipelined(in, n_in, out, out_cap, n_out, n_chunks);
+            return decode_pipelined(in, n_in, out, out_cap, n_out, chunk_bytes, n_chunks);
     }
     CK(cudaEventRecord(g.ev[4], g.stream));
     CK(cudaMemsetAsync((char *)g.stage_in + (in_cap - 16), 0, 32, g.stream));

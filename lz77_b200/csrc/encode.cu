@@ -398,9 +398,13 @@ long long encode_chunk_granule() { return (long long)kScanTile * kSegBytes; }
 // Encodes input bytes [lo, lo + n_chunk) (lo a multiple of encode_chunk_granule(),
 // hence of the block size) of a buffer whose earlier chunks were encoded by
 // earlier calls: tokens are appended behind the *pl.total tokens written so far.
+// phase 0: everything; phase 1: the search/parse kernel only; phase 2: the token
+// count scan and the bit-packer only (the host pipeline runs the searches of
+// consecutive chunks on alternating streams so their tails overlap).
 cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
                                 bool first, const Params &P, const EncodePlan &pl,
-                                uint32_t *d_out_words, cudaStream_t st, StageEvents *ev)
+                                uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
+                                int phase)
 {
     const uint8_t *d_in = d_in_base + lo;
     const long long seg0 = lo / kSegBytes;
@@ -419,9 +423,11 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
     const long long n_tiles = (n_chunk + tile_bytes - 1) / tile_bytes;
     const bool small_la = P.la <= 16;
 
-    if (first) cudaMemsetAsync(total, 0, 8, st);
+    if (first && phase != 1) cudaMemsetAsync(total, 0, 8, st);
     if (ev) cudaEventRecord(ev->e[0], st);
-    if (n_tiles > 0 && P.window <= 8191) {
+    if (phase == 2) {
+        // searched by an earlier phase-1 call
+    } else if (n_tiles > 0 && P.window <= 8191) {
         // small windows: bucketed search (search_bucket.cu)
         cudaError_t rc = launch_parse_bucket(d_in, n_chunk, P, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
@@ -442,6 +448,7 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
                                                             seg_ntok);
     }
     if (ev) cudaEventRecord(ev->e[1], st);
+    if (phase == 1) return cudaGetLastError();
     if (n_seg > 0) {
         scan_partial_kernel<<<(unsigned)n_part, kScanThreads, 0, st>>>(seg_ntok, n_seg, partial);
         scan_top_kernel<<<1, 1024, 0, st>>>(partial, n_part, total);
@@ -467,7 +474,7 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, 
 {
     const EncodePlan pl = encode_plan(scratch, n_in, P);
     *d_total_tokens = pl.total;
-    return launch_encode_chunk(d_in, 0, n_in, true, P, pl, d_out_words, st, ev);
+    return launch_encode_chunk(d_in, 0, n_in, true, P, pl, d_out_words, st, ev, 0);
 }
 
 int encode_launch_count(long long n_in)

@@ -31,7 +31,8 @@ EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P);
 long long encode_chunk_granule();
 cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
                                 bool first, const Params &P, const EncodePlan &pl,
-                                uint32_t *d_out_words, cudaStream_t st, StageEvents *ev);
+                                uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
+                                int phase);
 
 // bucketed longest-match search + greedy parse (search_bucket.cu)
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,

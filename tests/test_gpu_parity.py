@@ -216,7 +216,7 @@ def test_cli_cross_roundtrip_with_reference(lz, orc, tmp_path):
 @pytest.mark.parametrize("sb,la,n", [(4095, 15, 80 << 20), (1000, 20, (70 << 20) + 12_345),
                                      (4095, 15, (64 << 20) + 3), (1, 2, (33 << 20) + 1)])
 def test_host_chunked_encode_equals_device_encode(lz, orc, sb, la, n):
-    """The host entry point pipelines inputs above 32 MiB in chunks (H2D, kernels
+    """The host entry point pipelines inputs above 16 MiB in chunks (H2D, kernels
     and D2H overlapped); the stream must be bit-identical to the one-shot device
     encode, also when a chunk seam falls inside a byte (23- and 9-bit tokens)."""
     import torch
@@ -250,7 +250,7 @@ def test_pipelined_host_paths_small_chunks(lz, orc, sb, la):
             assert enc == spec, (kind, "chunked host encode")
             assert lz.decode(enc) == data
     finally:
-        api.set_host_chunk(32 << 20)
+        api.set_host_chunk(16 << 20)
 
 
 def _fuzz_cases(count=48, seed=2024):
