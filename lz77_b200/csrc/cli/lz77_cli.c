@@ -1,5 +1,5 @@
 /*
- * main.c -- command-line driver with the reference's surface (main.c:59-181):
+ * lz77_cli.c -- command-line driver with the reference's surface (main.c:59-181):
  *   lz77 -c|-d -i <in> -o <out> [-l 2..255] [-s 0..65535] [-h]
  * Same getopt string plus one additive option, -g <device>.  Same limits
  * (main.c:35-38), same messages and exit codes: every usage or open error

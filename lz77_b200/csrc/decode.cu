@@ -180,6 +180,10 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
 #ifndef LZ77_DEC_SLEEP_NS
 #define LZ77_DEC_SLEEP_NS 40
 #endif
+#ifndef LZ77_DEC_THREADS
+#define LZ77_DEC_THREADS 512
+#endif
+constexpr int kDecThreadsSmall = LZ77_DEC_THREADS;  // CTA size for 64 KiB tiles (3 CTAs/SM)
 constexpr int kDecSpins = LZ77_DEC_SPINS;        // polls without progress before backing off
 constexpr unsigned kDecSleepNs = LZ77_DEC_SLEEP_NS;
 
@@ -508,13 +512,13 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (tile_bytes <= 65536) {
-        auto kern = lz77_decode_tile_kernel<512, 3>;
+        auto kern = lz77_decode_tile_kernel<kDecThreadsSmall, 3>;
         cudaError_t rc =
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;
         long long grid = (long long)sms * 3;
         if (grid > n_run) grid = n_run;
-        kern<<<(unsigned)grid, 512, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
+        kern<<<(unsigned)grid, kDecThreadsSmall, smem, st>>>(d_in_words, n_words, n_tokens, P, tile_shift,
                                                  s.tile_tok, s.tile_pos, s.group_pos, tile_begin,
                                                  tile_end,
                                                  n_tiles_total, n_out_eff, d_out, s.tile_done,
