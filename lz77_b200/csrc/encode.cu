@@ -97,11 +97,9 @@ lz77_parse_kernel(const uint8_t *__restrict__ in, long long n, Params P, int his
 
         if (max_len > 0 && reach > 0) {
             const int lo_idx = p0 - reach;
-            uint32_t tgt[4] = {0, 0, 0, 0};
-            if (kSmallLA) {
+            uint32_t tgt[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) tgt[i] = lds_u32_unaligned(smem, p0 + 4 * i);
-            }
+            for (int i = 0; i < 4; i++) tgt[i] = lds_u32_unaligned(smem, p0 + 4 * i);
             const uint32_t b0x4 = (uint32_t)smem[p0] * 0x01010101u;
             int best_len = 0, best_q = 0;
 

@@ -7,7 +7,8 @@
 namespace lz77 {
 
 // Length of the common prefix of smem[q..] and smem[p0..], capped at max_len.
-// kSmallLA (LA <= 16): the lookahead is held in registers as tgt[0..3].
+// The first 16 lookahead bytes are held in registers as tgt[0..3]; with kSmallLA
+// (LA <= 16) that is the whole lookahead.
 template <bool kSmallLA>
 __device__ __forceinline__ int match_len(const uint8_t *smem, int q, int p0,
                                          const uint32_t (&tgt)[4], int max_len)
@@ -39,12 +40,25 @@ __device__ __forceinline__ int match_len(const uint8_t *smem, int q, int p0,
         }
         return min(l, max_len);
     } else {
-        int l = 0;
-        uint32_t a = w[0];
-        int wi = 1;
+        // LA > 16: the first 16 bytes against the registers (most candidates differ
+        // there), the rest word by word against shared memory
+        uint32_t a0 = w[0], a1 = w[1];
+        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+        if (x) return min((__ffs(x) - 1) >> 3, max_len);
+        uint32_t a2 = w[2];
+        x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+        if (x) return min(4 + ((__ffs(x) - 1) >> 3), max_len);
+        uint32_t a3 = w[3];
+        x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+        if (x) return min(8 + ((__ffs(x) - 1) >> 3), max_len);
+        uint32_t a = w[4];
+        x = __funnelshift_r(a3, a, sh) ^ tgt[3];
+        if (x) return min(12 + ((__ffs(x) - 1) >> 3), max_len);
+        int l = 16;
+        int wi = 5;
         while (l < max_len) {
             uint32_t b = w[wi++];
-            uint32_t x = __funnelshift_r(a, b, sh) ^ lds_u32_unaligned(smem, p0 + l);
+            x = __funnelshift_r(a, b, sh) ^ lds_u32_unaligned(smem, p0 + l);
             if (x) {
                 l += (__ffs(x) - 1) >> 3;
                 break;

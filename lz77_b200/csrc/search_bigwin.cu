@@ -258,15 +258,11 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                 const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (p0 & ~3));
                 const int sh = (p0 & 3) * 8;
                 const uint32_t a0 = w[0], a1 = w[1];
+                const uint32_t a2 = w[2], a3 = w[3], a4 = w[4];
                 tgt[0] = __funnelshift_r(a0, a1, sh);
-                if (kSmallLA) {
-                    const uint32_t a2 = w[2], a3 = w[3], a4 = w[4];
-                    tgt[1] = __funnelshift_r(a1, a2, sh);
-                    tgt[2] = __funnelshift_r(a2, a3, sh);
-                    tgt[3] = __funnelshift_r(a3, a4, sh);
-                } else {
-                    tgt[1] = tgt[2] = tgt[3] = 0;
-                }
+                tgt[1] = __funnelshift_r(a1, a2, sh);
+                tgt[2] = __funnelshift_r(a2, a3, sh);
+                tgt[3] = __funnelshift_r(a3, a4, sh);
             }
             const uint32_t b0 = tgt[0] & 0xffu;
             int best_len = 0, best_q = 0;

@@ -107,16 +107,28 @@ __device__ __forceinline__ int match_len_s(uint32_t sdata, int q, int p0,
         }
         return min(l, max_len);
     } else {
-        int l = 0;
-        uint32_t a = lds32(w);
-        uint32_t wa = w + 4;
+        // LA > 16: first the 16 register-resident bytes, then word by word
+        const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
+        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+        if (x) return min((__ffs(x) - 1) >> 3, max_len);
+        const uint32_t a2 = lds32(w + 8);
+        x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+        if (x) return min(4 + ((__ffs(x) - 1) >> 3), max_len);
+        const uint32_t a3 = lds32(w + 12);
+        x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+        if (x) return min(8 + ((__ffs(x) - 1) >> 3), max_len);
+        uint32_t a = lds32(w + 16);
+        x = __funnelshift_r(a3, a, sh) ^ tgt[3];
+        if (x) return min(12 + ((__ffs(x) - 1) >> 3), max_len);
+        int l = 16;
+        uint32_t wa = w + 20;
         while (l < max_len) {
             const uint32_t b = lds32(wa);
             wa += 4;
             const int pi = p0 + l;
             const uint32_t pw = sdata + (uint32_t)(pi & ~3);
             const uint32_t t = __funnelshift_r(lds32(pw), lds32(pw + 4), (pi & 3) * 8);
-            const uint32_t x = __funnelshift_r(a, b, sh) ^ t;
+            x = __funnelshift_r(a, b, sh) ^ t;
             if (x) {
                 l += (__ffs(x) - 1) >> 3;
                 break;
@@ -314,15 +326,11 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                         const uint32_t w = sdata + (uint32_t)(p0 & ~3);
                         const int sh = (p0 & 3) * 8;
                         const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
+                        const uint32_t a2 = lds32(w + 8), a3 = lds32(w + 12), a4 = lds32(w + 16);
                         tgt[0] = __funnelshift_r(a0, a1, sh);
-                        if (kSmallLA) {
-                            const uint32_t a2 = lds32(w + 8), a3 = lds32(w + 12), a4 = lds32(w + 16);
-                            tgt[1] = __funnelshift_r(a1, a2, sh);
-                            tgt[2] = __funnelshift_r(a2, a3, sh);
-                            tgt[3] = __funnelshift_r(a3, a4, sh);
-                        } else {
-                            tgt[1] = tgt[2] = tgt[3] = 0;
-                        }
+                        tgt[1] = __funnelshift_r(a1, a2, sh);
+                        tgt[2] = __funnelshift_r(a2, a3, sh);
+                        tgt[3] = __funnelshift_r(a3, a4, sh);
                     }
                     const int key = pair_key(tgt[0], tgt[0] >> 8);
                     const int bs = (int)lds16(sbstart + 2u * key);
