@@ -259,16 +259,18 @@ scan_apply_kernel(const uint32_t *__restrict__ in, long long n,
 // first and last word of a segment may be shared with its neighbours and are
 // OR-ed into words lz77_pack_prepare_kernel zeroed.
 
+template <int kT>  // token width when known at compile time (24, 32), 0 = any
 __device__ __forceinline__ uint32_t gather_word(const uint32_t *__restrict__ toks, int n_tok,
-                                                long long rel_lo, int tbits)
+                                                int rel_lo, int tbits_rt)
 {
+    const int tbits = kT ? kT : tbits_rt;  // divisions by a constant when kT != 0
     // rel_lo: bit offset of the word relative to the segment's first token bit
-    int t0 = rel_lo <= 0 ? 0 : (int)(rel_lo / tbits);
-    int t1 = (int)((rel_lo + 31) / tbits);
+    int t0 = rel_lo <= 0 ? 0 : rel_lo / tbits;
+    int t1 = (rel_lo + 31) / tbits;
     if (t1 > n_tok - 1) t1 = n_tok - 1;
     uint32_t val = 0;
     for (int t = t0; t <= t1; t++) {
-        const int tb = (int)((long long)t * tbits - rel_lo);  // in (-tbits, 32)
+        const int tb = t * tbits - rel_lo;  // in (-tbits, 32)
         const uint32_t v = __ldg(toks + t);
         val |= tb >= 0 ? v << tb : v >> (-tb);
     }
@@ -299,6 +301,7 @@ __global__ void lz77_pack_prepare_kernel(const uint32_t *__restrict__ seg_ntok,
     if (!shared_with_earlier_chunk) out[(b1 - 1) >> 5] = 0;
 }
 
+template <int kT>
 __global__ void __launch_bounds__(256)
 lz77_pack_kernel(const uint32_t *__restrict__ tok_tmp, const uint32_t *__restrict__ seg_ntok,
                  const unsigned long long *__restrict__ prefix, long long n_seg, Params P,
@@ -310,7 +313,7 @@ lz77_pack_kernel(const uint32_t *__restrict__ tok_tmp, const uint32_t *__restric
     const int nt = (int)seg_ntok[s];
     if (!nt) return;
     const uint32_t *toks = tok_tmp + s * kSegBytes;
-    const int T = P.tbits;
+    const int T = kT ? kT : P.tbits;
     const long long b0 = kHeaderBits + (long long)T * (long long)prefix[s];
     const long long b1 = b0 + (long long)T * nt;
     const long long w_first = b0 >> 5, w_last = (b1 - 1) >> 5;
@@ -320,17 +323,17 @@ lz77_pack_kernel(const uint32_t *__restrict__ tok_tmp, const uint32_t *__restric
         const bool interior = (w4 << 5) >= b0 && ((w4 + 4) << 5) <= b1;
         if (interior) {
             uint4 v;
-            v.x = gather_word(toks, nt, ((w4 + 0) << 5) - b0, T);
-            v.y = gather_word(toks, nt, ((w4 + 1) << 5) - b0, T);
-            v.z = gather_word(toks, nt, ((w4 + 2) << 5) - b0, T);
-            v.w = gather_word(toks, nt, ((w4 + 3) << 5) - b0, T);
+            v.x = gather_word<kT>(toks, nt, (int)(((w4 + 0) << 5) - b0), T);
+            v.y = gather_word<kT>(toks, nt, (int)(((w4 + 1) << 5) - b0), T);
+            v.z = gather_word<kT>(toks, nt, (int)(((w4 + 2) << 5) - b0), T);
+            v.w = gather_word<kT>(toks, nt, (int)(((w4 + 3) << 5) - b0), T);
             *reinterpret_cast<uint4 *>(out + w4) = v;  // coalesced 128-bit store
         } else {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const long long w = w4 + i;
                 if (w < w_first || w > w_last) continue;
-                const uint32_t val = gather_word(toks, nt, (w << 5) - b0, T);
+                const uint32_t val = gather_word<kT>(toks, nt, (int)((w << 5) - b0), T);
                 if ((w << 5) >= b0 && ((w + 1) << 5) <= b1)
                     out[w] = val;
                 else
@@ -458,9 +461,12 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
         const long long nthreads = n_seg > 0 ? n_seg : 1;
         lz77_pack_prepare_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(
             seg_ntok, prefix, n_seg, P, first, d_out_words);
-        if (n_seg > 0)
-            lz77_pack_kernel<<<(unsigned)((n_seg + 7) / 8), 256, 0, st>>>(
-                tok_tmp, seg_ntok, prefix, n_seg, P, d_out_words);
+        if (n_seg > 0) {
+            auto pack = P.tbits == 24 ? lz77_pack_kernel<24>
+                                      : P.tbits == 32 ? lz77_pack_kernel<32> : lz77_pack_kernel<0>;
+            pack<<<(unsigned)((n_seg + 7) / 8), 256, 0, st>>>(tok_tmp, seg_ntok, prefix, n_seg, P,
+                                                               d_out_words);
+        }
     }
     if (ev) cudaEventRecord(ev->e[3], st);
     return cudaGetLastError();
