@@ -98,29 +98,107 @@ static unsigned char *slurp(FILE *f, long *n_out)
     return buf;
 }
 
+/* Bytes of input encoded per library call.  The encoder's blocks are independent,
+ * so the stream of a large file is the streams of its pieces back to back: the
+ * file never has to fit in (pinned) memory, like the reference's O(1)-memory
+ * window loop (lz77.c:78,113-129).  A multiple of every block size. */
+static long piece_bytes(void)
+{
+    const char *e = getenv("LZ77_CLI_PIECE_MIB"); /* test hook */
+    long mib = e ? atol(e) : 1024;
+    if (mib < 1)
+        mib = 1;
+    return mib << 20;
+}
+
+/* appends `nbits` bits (LSB-first, bitio.c:203-239) of src to the output file;
+ * *acc / *acc_bits carry the bits of the last, still incomplete byte */
+static int put_bits(FILE *f, const unsigned char *src, long nbits, unsigned *acc, int *acc_bits)
+{
+    long nbytes = nbits >> 3, i;
+    int tail = (int)(nbits & 7);
+    if (*acc_bits == 0) {
+        if (nbytes > 0 && fwrite(src, 1, (size_t)nbytes, f) != (size_t)nbytes)
+            return -1;
+    } else {
+        /* the stream position is inside a byte: shift everything by acc_bits */
+        enum { BUF = 1 << 16 };
+        static unsigned char buf[BUF];
+        long done = 0;
+        while (done < nbytes) {
+            long n = nbytes - done < BUF ? nbytes - done : BUF;
+            for (i = 0; i < n; i++) {
+                unsigned v = *acc | ((unsigned)src[done + i] << *acc_bits);
+                buf[i] = (unsigned char)v;
+                *acc = v >> 8;
+            }
+            if (fwrite(buf, 1, (size_t)n, f) != (size_t)n)
+                return -1;
+            done += n;
+        }
+    }
+    if (tail) {
+        unsigned v = *acc | ((unsigned)(src[nbytes] & ((1u << tail) - 1u)) << *acc_bits);
+        int total = *acc_bits + tail;
+        if (total >= 8) {
+            if (fputc((int)(v & 0xff), f) == EOF)
+                return -1;
+            v >>= 8;
+            total -= 8;
+        }
+        *acc = v;
+        *acc_bits = total;
+    }
+    return 0;
+}
+
 void encode(FILE *file, struct bitFILE *out, int la, int sb)
 {
-    long n_in = 0, n_out = 0, cap;
-    unsigned char *in, *obuf;
-    int rc;
+    const long piece = piece_bytes();
+    const int esb = sb == -1 ? LZ77_DEFAULT_SB : sb, ela = la == -1 ? LZ77_DEFAULT_LA : la;
+    const int tbits = lz77_token_bits(esb, ela);
+    long cap = 0;
+    unsigned char *in, *obuf = NULL;
+    unsigned acc = 0;
+    int acc_bits = 0, first = 1, rc;
 
     bind_device();
-    in = slurp(file, &n_in);
-    if (in == NULL) {
-        printf("Error loading the data in the window.\n"); /* lz77.c:79-82 */
-        return;
+    in = lz77_gpu_host_alloc(piece);
+    if (in == NULL)
+        die("allocating the input buffer", LZ77_E_NOMEM);
+    for (;;) {
+        long n_out = 0, n_tokens;
+        long n_in = (long)fread(in, 1, (size_t)piece, file);
+        if (ferror(file)) {
+            printf("Error loading the data in the window.\n"); /* lz77.c:79-82 */
+            break;
+        }
+        if (n_in == 0 && !first)
+            break;
+        if (obuf == NULL) {
+            cap = lz77_gpu_encode_bound(n_in < piece ? n_in : piece, sb, la) + 16;
+            obuf = lz77_gpu_host_alloc(cap);
+            if (obuf == NULL)
+                die("allocating the output buffer", LZ77_E_NOMEM);
+        }
+        rc = lz77_gpu_encode(in, n_in, sb, la, obuf, cap, &n_out);
+        if (rc != LZ77_OK)
+            die("encoding", rc);
+        if (first && fwrite(obuf, 1, 4, out->file) != 4) /* header, lz77.c:74-75 */
+            perror("Writing output file");
+        /* padding is < 8 < T bits, so the token count follows from the size */
+        n_tokens = ((n_out - 4) * 8) / tbits;
+        if (put_bits(out->file, obuf + 4, n_tokens * tbits, &acc, &acc_bits) != 0)
+            perror("Writing output file");
+        first = 0;
+        if (n_in < piece)
+            break;
     }
-    cap = lz77_gpu_encode_bound(n_in, sb, la) + 16;
-    obuf = lz77_gpu_host_alloc(cap);
-    if (obuf == NULL)
-        die("allocating the output buffer", LZ77_E_NOMEM);
-    rc = lz77_gpu_encode(in, n_in, sb, la, obuf, cap, &n_out);
-    if (rc != LZ77_OK)
-        die("encoding", rc);
-    if (fwrite(obuf, 1, (size_t)n_out, out->file) != (size_t)n_out)
-        perror("Writing output file");
+    if (acc_bits > 0) /* zero padded last byte, bitio.c:180-182 */
+        fputc((int)(acc & 0xff), out->file);
     lz77_gpu_host_free(in);
-    lz77_gpu_host_free(obuf);
+    if (obuf != NULL)
+        lz77_gpu_host_free(obuf);
 }
 
 void decode(struct bitFILE *file, FILE *out)

@@ -334,3 +334,28 @@ def test_c_abi_error_codes(lz):
     # the library still works afterwards
     assert lz.decode(stream.tobytes()) == data.tobytes()
     assert lib.lz77_gpu_strerror(api.E_STREAM).decode() == "malformed stream"
+
+
+@pytest.mark.parametrize("args", [[], ["-s", "1000", "-l", "20"], ["-s", "65535", "-l", "255"],
+                                  ["-s", "1", "-l", "2"]])
+def test_cli_streams_large_files_in_pieces(lz, orc, tmp_path, args):
+    """The command-line encoder reads its input in pieces (1 GiB by default, 1 MiB
+    here) and appends their token payloads bit-exactly: the file is the same as
+    when the whole input goes through one library call."""
+    from lz77_b200 import synth
+    cli = ROOT / "lz77_b200" / "bin" / "lz77"
+    data = synth.zipf_text(5 * (1 << 20) + 777, seed=55).numpy().tobytes()
+    fin = tmp_path / "in.bin"
+    fin.write_bytes(data)
+    one, pieces, back = tmp_path / "one.lz", tmp_path / "pieces.lz", tmp_path / "back.bin"
+    subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(one), *args], check=True)
+    env = dict(os.environ, LZ77_CLI_PIECE_MIB="1")
+    subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(pieces), *args], check=True, env=env)
+    assert pieces.read_bytes() == one.read_bytes()
+    subprocess.run([str(cli), "-d", "-i", str(pieces), "-o", str(back)], check=True)
+    assert back.read_bytes() == data
+    # empty input: header only
+    empty = tmp_path / "empty.bin"
+    empty.write_bytes(b"")
+    subprocess.run([str(cli), "-c", "-i", str(empty), "-o", str(one), *args], check=True, env=env)
+    assert len(one.read_bytes()) == 4
