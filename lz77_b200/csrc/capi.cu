@@ -28,6 +28,7 @@ struct Context {
     cudaStream_t aux = nullptr;         // extra compute streams of the chunked host paths
     cudaStream_t aux2 = nullptr;
     unsigned long long *pinned_totals = nullptr;  // running token count per host chunk
+    std::vector<cudaEvent_t> pool;      // untimed events of the chunked host paths (reused)
     void *scratch = nullptr;
     size_t scratch_cap = 0;
     void *stage_in = nullptr;   // device staging for the host entry points
@@ -60,6 +61,17 @@ int fail_cuda(cudaError_t rc, const char *what)
         cudaError_t rc_ = (call);                         \
         if (rc_ != cudaSuccess) return fail_cuda(rc_, #call); \
     } while (0)
+
+// the first n events of the pool (created on demand, destroyed at shutdown)
+cudaEvent_t *pool_events(size_t n)
+{
+    while (g.pool.size() < n) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        g.pool.push_back(e);
+    }
+    return g.pool.data();
+}
 
 int grow(void **buf, size_t *cap, size_t need)
 {
@@ -147,6 +159,7 @@ void lz77_gpu_shutdown(void)
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
     for (auto &e : g.ev) cudaEventDestroy(e);
+    for (auto &e : g.pool) cudaEventDestroy(e);
     if (g.scratch) cudaFree(g.scratch);
     if (g.stage_in) cudaFree(g.stage_in);
     if (g.stage_out) cudaFree(g.stage_out);
@@ -306,12 +319,9 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in, P));
         if (rc) return rc;
         const EncodePlan pl = encode_plan(g.scratch, n_in, P);
-        std::vector<cudaEvent_t> ev_in(n_chunks), ev_done(n_chunks), ev_parse(n_chunks);
-        for (long long c = 0; c < n_chunks; c++) {
-            CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&ev_parse[c], cudaEventDisableTiming));
-        }
+        cudaEvent_t *evp = pool_events((size_t)(3 * n_chunks));
+        if (!evp) return LZ77_E_CUDA;
+        cudaEvent_t *ev_in = evp, *ev_done = evp + n_chunks, *ev_parse = evp + 2 * n_chunks;
         // (the large-window search keeps its bucket tables in one scratch area, so its
         // chunks must not overlap)
         const bool split_search = P.window <= 8191;
@@ -372,11 +382,6 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         CK(cudaStreamSynchronize(g.stream));
         CK(cudaStreamSynchronize(g.aux));
         CK(cudaStreamSynchronize(g.aux2));
-        for (long long c = 0; c < n_chunks; c++) {
-            cudaEventDestroy(ev_in[c]);
-            cudaEventDestroy(ev_done[c]);
-            cudaEventDestroy(ev_parse[c]);
-        }
         if (result != LZ77_OK) return result;
         *n_out = done_bytes;
         memset(&g.last, 0, sizeof g.last);
@@ -491,12 +496,9 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
     rc = grow(&g.scratch, &g.scratch_cap, decode_scratch_bytes(K, P));
     if (rc) return rc;
 
-    std::vector<cudaEvent_t> ev_in(n_chunks), ev_scan(n_chunks), ev_tiles(n_chunks);
-    for (long long c = 0; c < n_chunks; c++) {
-        CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_scan[c], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_tiles[c], cudaEventDisableTiming));
-    }
+    cudaEvent_t *evp = pool_events((size_t)(3 * n_chunks));
+    if (!evp) return LZ77_E_CUDA;
+    cudaEvent_t *ev_in = evp, *ev_scan = evp + n_chunks, *ev_tiles = evp + 2 * n_chunks;
     const size_t in_cap = ((size_t)n_in + 15) & ~(size_t)15;
     CK(cudaMemsetAsync((char *)g.stage_in + (in_cap - 16), 0, 32, g.stream));
     CK(cudaEventRecord(g.ev[4], g.stream));
@@ -570,11 +572,6 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
     if (result == LZ77_OK) {
         CK(cudaMemcpy(g.pinned, d_info, sizeof(DecodeInfo), cudaMemcpyDeviceToHost));
         if (((const DecodeInfo *)g.pinned)->error) result = LZ77_E_STREAM;
-    }
-    for (long long c = 0; c < n_chunks; c++) {
-        cudaEventDestroy(ev_in[c]);
-        cudaEventDestroy(ev_scan[c]);
-        cudaEventDestroy(ev_tiles[c]);
     }
     *n_out = n_total;
     g.last.launches = (int)(2 * n_chunks);
