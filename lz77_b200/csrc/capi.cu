@@ -27,6 +27,7 @@ struct Context {
     cudaStream_t copy_out = nullptr;
     cudaStream_t aux = nullptr;         // extra compute streams of the chunked host paths
     cudaStream_t aux2 = nullptr;
+    cudaStream_t hi = nullptr;          // high-priority stream for the short kernels of a pipeline
     unsigned long long *pinned_totals = nullptr;  // running token count per host chunk
     std::vector<cudaEvent_t> pool;      // untimed events of the chunked host paths (reused)
     void *scratch = nullptr;
@@ -169,6 +170,7 @@ void lz77_gpu_shutdown(void)
     if (g.copy_out) cudaStreamDestroy(g.copy_out);
     if (g.aux) cudaStreamDestroy(g.aux);
     if (g.aux2) cudaStreamDestroy(g.aux2);
+    if (g.hi) cudaStreamDestroy(g.hi);
     cudaStreamDestroy(g.own_stream);
     g = Context();
 }
@@ -190,8 +192,18 @@ int lz77_gpu_init(int device)
     CK(cudaMallocHost((void **)&g.pinned, 256));
     CK(cudaStreamCreateWithFlags(&g.copy_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g.copy_out, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g.aux, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g.aux2, cudaStreamNonBlocking));
+    {
+        // The long kernels of the chunked host pipelines (search, tile decode) run on
+        // low-priority streams and the short ones that follow each chunk (token-count
+        // scan, bit-packer, token scan) on a high-priority stream: otherwise the queued
+        // search kernels of later chunks keep every SM slot busy and the packers -- and
+        // with them the D2H copies -- only run after the last search.
+        int lo_pri = 0, hi_pri = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CK(cudaStreamCreateWithPriority(&g.aux, cudaStreamNonBlocking, lo_pri));
+        CK(cudaStreamCreateWithPriority(&g.aux2, cudaStreamNonBlocking, lo_pri));
+        CK(cudaStreamCreateWithPriority(&g.hi, cudaStreamNonBlocking, hi_pri));
+    }
     CK(cudaMallocHost((void **)&g.pinned_totals, kMaxHostChunks * sizeof(unsigned long long)));
     g.device = device;
     g.ready = true;
@@ -314,7 +326,11 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
     const long long granule = encode_chunk_granule();
     long long chunk = kHostChunkBytes / granule * granule;
     if (chunk < granule) chunk = granule;
-    const long long n_chunks = (n_in + chunk - 1) / chunk;
+    // chunk boundaries: equal chunks (16 MiB unless lz77_gpu_set_host_chunk() says otherwise)
+    std::vector<long long> bounds(1, 0);
+    for (long long pos = chunk; pos < (long long)n_in; pos += chunk) bounds.push_back(pos);
+    bounds.push_back(n_in);
+    const long long n_chunks = (long long)bounds.size() - 1;
     if (n_chunks >= 2 && n_chunks <= kMaxHostChunks) {
         rc = grow(&g.scratch, &g.scratch_cap, encode_scratch_bytes(n_in, P));
         if (rc) return rc;
@@ -331,9 +347,10 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         CK(cudaStreamWaitEvent(g.copy_out, g.ev[4], 0));
         CK(cudaStreamWaitEvent(g.aux, g.ev[4], 0));
         CK(cudaStreamWaitEvent(g.aux2, g.ev[4], 0));
+        CK(cudaStreamWaitEvent(g.hi, g.ev[4], 0));
         for (long long c = 0; c < n_chunks; c++) {
-            const long long lo = c * chunk;
-            const long long len = (lo + chunk <= n_in) ? chunk : n_in - lo;
+            const long long lo = bounds[c];
+            const long long len = bounds[c + 1] - lo;
             CK(cudaMemcpyAsync((char *)g.stage_in + lo, in + lo, (size_t)len,
                                cudaMemcpyHostToDevice, g.copy_in));
             CK(cudaEventRecord(ev_in[c], g.copy_in));
@@ -345,18 +362,18 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
                                        (uint32_t *)g.stage_out, ps, nullptr, 1));
                 CK(cudaEventRecord(ev_parse[c], ps));
-                CK(cudaStreamWaitEvent(g.stream, ev_parse[c], 0));
+                CK(cudaStreamWaitEvent(g.hi, ev_parse[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, g.stream, nullptr, 2));
+                                       (uint32_t *)g.stage_out, g.hi, nullptr, 2));
             } else {
-                CK(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
+                CK(cudaStreamWaitEvent(g.hi, ev_in[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, g.stream, nullptr, 0));
+                                       (uint32_t *)g.stage_out, g.hi, nullptr, 0));
             }
-            CK(cudaMemcpyAsync(&g.pinned_totals[c], pl.total, 8, cudaMemcpyDeviceToHost,
-                               g.stream));
-            CK(cudaEventRecord(ev_done[c], g.stream));
+            CK(cudaMemcpyAsync(&g.pinned_totals[c], pl.total, 8, cudaMemcpyDeviceToHost, g.hi));
+            CK(cudaEventRecord(ev_done[c], g.hi));
         }
+        CK(cudaEventRecord(g.ev[5], g.hi));  // behind the last chunk's bit-packer
         long done_bytes = 0;
         int result = LZ77_OK;
         unsigned long long k = 0;
@@ -379,6 +396,7 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
             }
         }
         CK(cudaStreamSynchronize(g.copy_out));
+        CK(cudaStreamSynchronize(g.hi));
         CK(cudaStreamSynchronize(g.stream));
         CK(cudaStreamSynchronize(g.aux));
         CK(cudaStreamSynchronize(g.aux2));
@@ -387,6 +405,9 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         memset(&g.last, 0, sizeof g.last);
         g.last.launches = (int)n_chunks * encode_launch_count(chunk);
         g.last.n_tokens = (long)k;
+        // pipelined call: the stages overlap, so only the span of the compute stream
+        // (first H2D issued .. last bit-packer done) is reported, as the search time
+        if (g.timing) g.last.enc_search_ms = ms_between(g.ev[4], g.ev[5]);
         return LZ77_OK;
     }
 
@@ -505,6 +526,7 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
     CK(cudaStreamWaitEvent(g.copy_in, g.ev[4], 0));
     CK(cudaStreamWaitEvent(g.copy_out, g.ev[4], 0));
     CK(cudaStreamWaitEvent(g.aux, g.ev[4], 0));
+    CK(cudaStreamWaitEvent(g.hi, g.ev[4], 0));
 
     // queue every H2D copy and every scan; the scans need nothing from the host
     const long long granule = decode_scan_granule();
@@ -516,18 +538,18 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
         CK(cudaMemcpyAsync((char *)g.stage_in + lo, in + lo, (size_t)(hi - lo),
                            cudaMemcpyHostToDevice, g.copy_in));
         CK(cudaEventRecord(ev_in[c], g.copy_in));
-        CK(cudaStreamWaitEvent(g.stream, ev_in[c], 0));
+        CK(cudaStreamWaitEvent(g.hi, ev_in[c], 0));
         long long tok_hi = K;
         if (c + 1 < n_chunks) {
             tok_hi = ((hi - 4) * 8) / P.tbits / granule * granule;  // whole tokens, whole scan chunks
             if (tok_hi < tok_lo) tok_hi = tok_lo;
         }
         CK(launch_decode_scan_range((const uint32_t *)g.stage_in, hi, K, tok_lo, tok_hi, P,
-                                    g.scratch, &d_info, g.stream));
+                                    g.scratch, &d_info, g.hi));
         tok_lo = tok_hi;
         CK(cudaMemcpyAsync(&g.pinned_totals[c], &d_info->n_out, 8, cudaMemcpyDeviceToHost,
-                           g.stream));
-        CK(cudaEventRecord(ev_scan[c], g.stream));
+                           g.hi));
+        CK(cudaEventRecord(ev_scan[c], g.hi));
     }
 
     // as the scans finish: decode the tiles they completed, copy them back
@@ -568,6 +590,7 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
     }
     CK(cudaStreamSynchronize(g.aux));
     CK(cudaStreamSynchronize(g.copy_out));
+    CK(cudaStreamSynchronize(g.hi));
     CK(cudaStreamSynchronize(g.stream));
     if (result == LZ77_OK) {
         CK(cudaMemcpy(g.pinned, d_info, sizeof(DecodeInfo), cudaMemcpyDeviceToHost));

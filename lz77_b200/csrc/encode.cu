@@ -394,10 +394,12 @@ EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P)
     return pl;
 }
 
-long long encode_chunk_granule() { return (long long)kScanTile * kSegBytes; }
+// chunks of a chunked encode must start on a block boundary (the largest block size)
+long long encode_chunk_granule() { return 131072; }
 
 // Encodes input bytes [lo, lo + n_chunk) (lo a multiple of encode_chunk_granule(),
-// hence of the block size) of a buffer whose earlier chunks were encoded by
+// hence of the block size; the scans of successive chunks run in stream order, so a
+// chunk may reuse the last partial-sum slot of its predecessor) of a buffer whose earlier chunks were encoded by
 // earlier calls: tokens are appended behind the *pl.total tokens written so far.
 // phase 0: everything; phase 1: the search/parse kernel only; phase 2: the token
 // count scan and the bit-packer only (the host pipeline runs the searches of

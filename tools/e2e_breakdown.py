@@ -30,10 +30,12 @@ for chunk_mib in (0, 8, 16, 32, 64):
         t0 = time.perf_counter()
         c = api.encode_into(h_in.ptr, n, h_stream.ptr, cap)
         t1 = time.perf_counter()
+        span = api.last_timing()["enc_search_ms"]
         m = api.decode_into(h_stream.ptr, c, h_out.ptr, n)
         t2 = time.perf_counter()
         te += t1 - t0
         td += t2 - t1
     assert m == n and (h_out.array[:n] == h_in.array).all()
-    print(f"chunk {chunk_mib:3d} MiB: encode {te / reps * 1e3:6.2f} ms ({n / (te / reps) / 1e9:5.1f} GB/s)  "
+    print(f"chunk {chunk_mib:3d} MiB: encode {te / reps * 1e3:6.2f} ms (compute-stream span {span:6.2f} ms, "
+          f"{n / (te / reps) / 1e9:5.1f} GB/s)  "
           f"decode {td / reps * 1e3:6.2f} ms ({n / (td / reps) / 1e9:5.1f} GB/s)")
