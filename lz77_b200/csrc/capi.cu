@@ -28,7 +28,8 @@ struct Context {
     cudaStream_t aux = nullptr;         // extra compute streams of the chunked host paths
     cudaStream_t aux2 = nullptr;
     cudaStream_t hi = nullptr;          // high-priority stream for the short kernels of a pipeline
-    unsigned long long *pinned_totals = nullptr;  // running token count per host chunk
+    unsigned long long *pinned_totals = nullptr;  // running count per host chunk, written by the
+    unsigned long long *pinned_totals_dev = nullptr;  // kernels through this device alias
     std::vector<cudaEvent_t> pool;      // untimed events of the chunked host paths (reused)
     void *scratch = nullptr;
     size_t scratch_cap = 0;
@@ -204,7 +205,9 @@ int lz77_gpu_init(int device)
         CK(cudaStreamCreateWithPriority(&g.aux2, cudaStreamNonBlocking, lo_pri));
         CK(cudaStreamCreateWithPriority(&g.hi, cudaStreamNonBlocking, hi_pri));
     }
-    CK(cudaMallocHost((void **)&g.pinned_totals, kMaxHostChunks * sizeof(unsigned long long)));
+    CK(cudaHostAlloc((void **)&g.pinned_totals, kMaxHostChunks * sizeof(unsigned long long),
+                     cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&g.pinned_totals_dev, g.pinned_totals, 0));
     g.device = device;
     g.ready = true;
     memset(&g.last, 0, sizeof g.last);
@@ -360,17 +363,16 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
                 cudaStream_t ps = (c & 1) ? g.aux2 : g.aux;
                 CK(cudaStreamWaitEvent(ps, ev_in[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, ps, nullptr, 1));
+                                       (uint32_t *)g.stage_out, ps, nullptr, 1, nullptr));
                 CK(cudaEventRecord(ev_parse[c], ps));
                 CK(cudaStreamWaitEvent(g.hi, ev_parse[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, g.hi, nullptr, 2));
+                                       (uint32_t *)g.stage_out, g.hi, nullptr, 2, &g.pinned_totals_dev[c]));
             } else {
                 CK(cudaStreamWaitEvent(g.hi, ev_in[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, g.hi, nullptr, 0));
+                                       (uint32_t *)g.stage_out, g.hi, nullptr, 0, &g.pinned_totals_dev[c]));
             }
-            CK(cudaMemcpyAsync(&g.pinned_totals[c], pl.total, 8, cudaMemcpyDeviceToHost, g.hi));
             CK(cudaEventRecord(ev_done[c], g.hi));
         }
         CK(cudaEventRecord(g.ev[5], g.hi));  // behind the last chunk's bit-packer
@@ -528,6 +530,9 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
     CK(cudaStreamWaitEvent(g.aux, g.ev[4], 0));
     CK(cudaStreamWaitEvent(g.hi, g.ev[4], 0));
 
+    // the scan kernels write the output position behind their last token straight into
+    // pinned memory; a chunk that completes no scan chunk leaves the sentinel
+    for (long long c = 0; c < n_chunks; c++) g.pinned_totals[c] = ~0ull;
     // queue every H2D copy and every scan; the scans need nothing from the host
     const long long granule = decode_scan_granule();
     DecodeInfo *d_info = nullptr;
@@ -545,19 +550,18 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
             if (tok_hi < tok_lo) tok_hi = tok_lo;
         }
         CK(launch_decode_scan_range((const uint32_t *)g.stage_in, hi, K, tok_lo, tok_hi, P,
-                                    g.scratch, &d_info, g.hi));
+                                    g.scratch, &d_info, g.hi, &g.pinned_totals_dev[c]));
         tok_lo = tok_hi;
-        CK(cudaMemcpyAsync(&g.pinned_totals[c], &d_info->n_out, 8, cudaMemcpyDeviceToHost,
-                           g.hi));
         CK(cudaEventRecord(ev_scan[c], g.hi));
     }
 
     // as the scans finish: decode the tiles they completed, copy them back
-    long long tiles_done = 0, n_total = 0;
+    long long tiles_done = 0, n_total = 0, pos_seen = 0;
     int result = LZ77_OK;
     for (long long c = 0; c < n_chunks; c++) {
         CK(cudaEventSynchronize(ev_scan[c]));
-        const long long pos = (long long)g.pinned_totals[c];
+        if (g.pinned_totals[c] != ~0ull) pos_seen = (long long)g.pinned_totals[c];
+        const long long pos = pos_seen;
         const bool last = c + 1 == n_chunks;
         long long tile_end;
         if (last) {

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(kDsThreads)
 lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
                         Params P, int tile_shift, unsigned long long *status,
                         long long *__restrict__ tile_tok, long long *__restrict__ tile_pos,
-                        uint32_t *__restrict__ group_pos, unsigned int *tickets, DecodeInfo *info)
+                        uint32_t *__restrict__ group_pos, unsigned int *tickets, DecodeInfo *info,
+                        unsigned long long *host_n_out /* mapped pinned memory, may be null */)
 {
     __shared__ long long s_chunk;
     __shared__ unsigned long long s_warp_tot[kDsThreads / 32];
@@ -166,7 +167,14 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
             tile_tok[j] = k;
             tile_pos[j] = pos;
         }
-        if (k == n_tokens - 1) info->n_out = (unsigned long long)(pos + L[r]);
+        if (k == n_tokens - 1) {
+            info->n_out = (unsigned long long)(pos + L[r]);
+            if (host_n_out) {  // read by the chunked host path without a D2H memcpy
+                *reinterpret_cast<volatile unsigned long long *>(host_n_out) =
+                    (unsigned long long)(pos + L[r]);
+                __threadfence_system();
+            }
+        }
     }
 }
 
@@ -459,7 +467,7 @@ int decode_launch_count(bool with_copy) { return with_copy ? 2 : 1; }
 cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_bytes,
                                      long long n_tokens, long long tok_begin, long long tok_end,
                                      const Params &P, void *scratch, DecodeInfo **d_info,
-                                     cudaStream_t st)
+                                     cudaStream_t st, unsigned long long *host_n_out)
 {
     DecodeScratch s = carve_decode(scratch, n_tokens, P);
     *d_info = s.info;
@@ -472,7 +480,7 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
     if (n_chunks > 0)
         lz77_decode_scan_kernel<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(
             d_in_words, n_words, tok_end, P, P.block_shift, s.status, s.tile_tok, s.tile_pos,
-            s.group_pos, s.tickets, s.info);
+            s.group_pos, s.tickets, s.info, host_n_out);
     return cudaGetLastError();
 }
 
@@ -483,7 +491,7 @@ cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
                                DecodeInfo **d_info, cudaStream_t st)
 {
     return launch_decode_scan_range(d_in_words, n_in_bytes, n_tokens, 0, n_tokens, P, scratch,
-                                    d_info, st);
+                                    d_info, st, nullptr);
 }
 
 // Pass 2 over output tiles [tile_begin, tile_end).  `last` is false for a partial

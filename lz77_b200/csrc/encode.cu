@@ -209,7 +209,8 @@ scan_partial_kernel(const uint32_t *__restrict__ in, long long n,
 
 __global__ void __launch_bounds__(1024)
 scan_top_kernel(unsigned long long *__restrict__ partial, long long n_partial,
-                unsigned long long *__restrict__ grand_total)
+                unsigned long long *__restrict__ grand_total,
+                unsigned long long *host_total /* mapped pinned memory, may be null */)
 {
     __shared__ unsigned long long total;
     // *grand_total carries the token count of the chunks encoded before this one
@@ -223,7 +224,15 @@ scan_top_kernel(unsigned long long *__restrict__ partial, long long n_partial,
         carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *grand_total = carry;
+    if (threadIdx.x == 0) {
+        *grand_total = carry;
+        // the chunked host path reads the running count straight from pinned memory: a
+        // D2H memcpy of 8 bytes would queue behind the bulk output copies
+        if (host_total) {
+            *reinterpret_cast<volatile unsigned long long *>(host_total) = carry;
+            __threadfence_system();
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kScanThreads)
@@ -407,7 +416,7 @@ long long encode_chunk_granule() { return 131072; }
 cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
                                 bool first, const Params &P, const EncodePlan &pl,
                                 uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
-                                int phase)
+                                int phase, unsigned long long *host_total)
 {
     const uint8_t *d_in = d_in_base + lo;
     const long long seg0 = lo / kSegBytes;
@@ -454,7 +463,7 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
     if (phase == 1) return cudaGetLastError();
     if (n_seg > 0) {
         scan_partial_kernel<<<(unsigned)n_part, kScanThreads, 0, st>>>(seg_ntok, n_seg, partial);
-        scan_top_kernel<<<1, 1024, 0, st>>>(partial, n_part, total);
+        scan_top_kernel<<<1, 1024, 0, st>>>(partial, n_part, total, host_total);
         scan_apply_kernel<<<(unsigned)n_part, kScanThreads, 0, st>>>(seg_ntok, n_seg, partial,
                                                                       prefix);
     }
@@ -480,7 +489,7 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, 
 {
     const EncodePlan pl = encode_plan(scratch, n_in, P);
     *d_total_tokens = pl.total;
-    return launch_encode_chunk(d_in, 0, n_in, true, P, pl, d_out_words, st, ev, 0);
+    return launch_encode_chunk(d_in, 0, n_in, true, P, pl, d_out_words, st, ev, 0, nullptr);
 }
 
 int encode_launch_count(long long n_in)

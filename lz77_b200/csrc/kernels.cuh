@@ -32,7 +32,7 @@ long long encode_chunk_granule();
 cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
                                 bool first, const Params &P, const EncodePlan &pl,
                                 uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
-                                int phase);
+                                int phase, unsigned long long *host_total);
 
 // bucketed longest-match search + greedy parse (search_bucket.cu)
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
@@ -63,7 +63,7 @@ long long decode_scan_granule();
 cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_bytes,
                                      long long n_tokens, long long tok_begin, long long tok_end,
                                      const Params &P, void *scratch, DecodeInfo **d_info,
-                                     cudaStream_t st);
+                                     cudaStream_t st, unsigned long long *host_n_out);
 cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in_bytes,
                                       long long n_tokens, long long tile_begin,
                                       long long tile_end, bool last, long long n_out,
