@@ -276,6 +276,8 @@ def encode_tensor(src, la: int = -1, sb: int = -1, out=None):
     ``round16(encode_bound(n))`` bytes."""
     import torch
     assert src.is_cuda and src.dtype == torch.uint8 and src.is_contiguous()
+    if src.data_ptr() % 16:
+        raise Lz77Error(E_ARG, "device buffers must be 16-byte aligned (clone the view)")
     init(src.device.index)
     lib = load_library()
     n_in = src.numel()

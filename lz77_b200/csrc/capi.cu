@@ -5,6 +5,7 @@
 // host<->device copies for the host-buffer entry points, CUDA-event timing of
 // every stage.  No CPU implementation of the codec lives here: without a CUDA
 // device every compute entry point fails with LZ77_E_NODEVICE.
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -280,6 +281,8 @@ int lz77_gpu_encode_device(const void *d_in, long n_in, int sb, int la, void *d_
     Params P;
     if (make_params(sb, la, &P) != LZ77_OK || n_in < 0 || !d_out || (n_in > 0 && !d_in) || !n_out)
         return LZ77_E_ARG;
+    // the kernels move 128-bit words and TMA bulk copies: 16-byte aligned buffers only
+    if ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) return LZ77_E_ARG;
     const long bound = lz77_gpu_encode_bound(n_in, P.sb, P.la);
     if (out_cap < ((bound + 15) & ~15L)) return LZ77_E_SPACE;
     CK(cudaSetDevice(g.device));
@@ -456,6 +459,7 @@ int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_toke
 {
     if (!g.ready) return LZ77_E_NODEVICE;
     if (n_in < 0 || !d_in || !n_out) return LZ77_E_ARG;
+    if (((uintptr_t)d_in) & 15) return LZ77_E_ARG;  // 16-byte aligned buffers only
     if (n_in < 4) return LZ77_E_STREAM;
     CK(cudaSetDevice(g.device));
     unsigned char hdr[4];
@@ -623,7 +627,7 @@ int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_ca
     if (rc) return rc;
     *n_out = n;
     if (n == 0) return LZ77_OK;
-    if (!d_out) return LZ77_E_ARG;
+    if (!d_out || (((uintptr_t)d_out) & 15)) return LZ77_E_ARG;
     if (out_cap < n) return LZ77_E_SPACE;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
     CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, P, g.scratch, (uint8_t *)d_out,

@@ -359,3 +359,23 @@ def test_cli_streams_large_files_in_pieces(lz, orc, tmp_path, args):
     empty.write_bytes(b"")
     subprocess.run([str(cli), "-c", "-i", str(empty), "-o", str(one), *args], check=True, env=env)
     assert len(one.read_bytes()) == 4
+
+
+def test_device_buffers_must_be_aligned(lz):
+    """The device entry points move 128-bit words / TMA bulk copies: a misaligned
+    pointer is refused, not dereferenced."""
+    import ctypes as C
+    import torch
+    from lz77_b200 import api
+    buf = torch.zeros(4096 + 64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(api.encode_bound(4096) + 64, dtype=torch.uint8, device="cuda")
+    n, k = C.c_long(0), C.c_long(0)
+    lib = api.load_library()
+    assert lib.lz77_gpu_encode_device(buf.data_ptr() + 1, 4096, -1, -1, out.data_ptr(), out.numel(),
+                                      C.byref(n), C.byref(k)) == api.E_ARG
+    assert lib.lz77_gpu_encode_device(buf.data_ptr(), 4096, -1, -1, out.data_ptr() + 4,
+                                      out.numel() - 16, C.byref(n), C.byref(k)) == api.E_ARG
+    with pytest.raises(api.Lz77Error):
+        lz.encode_tensor(buf[1:])
+    s, _ = lz.encode_tensor(buf[:4096])
+    assert torch.equal(lz.decode_tensor(s), buf[:4096])
