@@ -379,3 +379,17 @@ def test_device_buffers_must_be_aligned(lz):
         lz.encode_tensor(buf[1:])
     s, _ = lz.encode_tensor(buf[:4096])
     assert torch.equal(lz.decode_tensor(s), buf[:4096])
+
+
+@pytest.mark.parametrize("kind,sb,la,tol", [("zipf_text", 4095, 15, 0.02), ("log_like", 4095, 15, 0.02),
+                                            ("random", 4095, 15, 0.02), ("zipf_text", 65535, 255, 0.08)])
+def test_compressed_size_close_to_reference(lz, orc, kind, sb, la, tol):
+    """Block cuts (64 / 128 KiB) and parse restarts (1 KiB) are the only reasons the
+    stream is longer than the reference's: within 2 % at the default parameters,
+    8 % at the 64 KiB window."""
+    from lz77_b200 import synth
+    data = synth.make(kind, 3 << 20, seed=61).numpy().tobytes()
+    ours = len(lz.encode(data, la=la, sb=sb))
+    ref = len(orc.ref_encode(data, sb, la))
+    assert ours >= ref * 0.999          # an exhaustive greedy parse cannot be beaten by blocks
+    assert ours <= ref * (1 + tol), (ours, ref)
