@@ -394,3 +394,19 @@ def test_compressed_size_close_to_reference(lz, orc, kind, sb, la, tol):
     ref = len(orc.ref_encode(data, sb, la))
     assert ours >= ref * 0.999          # an exhaustive greedy parse cannot be beaten by blocks
     assert ours <= ref * (1 + tol), (ours, ref)
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (1000, 20), (65535, 255)])
+@pytest.mark.parametrize("n", [(16 << 20) + 1, (32 << 20) - 1, (48 << 20) + 123_457])
+def test_host_pipeline_chunk_seams(lz, sb, la, n):
+    """Inputs that end just past / just before a 16 MiB host chunk: the pipelined
+    host encode must equal the one-shot device encode bit for bit, and the
+    pipelined host decode must return the input."""
+    import torch
+    from lz77_b200 import synth
+    src = synth.zipf_text(n, seed=71, device="cuda")
+    dev_stream, _ = lz.encode_tensor(src, la=la, sb=sb)
+    host = src.cpu().numpy()
+    enc = lz.encode(host, la=la, sb=sb)
+    assert enc == dev_stream.cpu().numpy().tobytes()
+    assert lz.decode(enc) == host.tobytes()
