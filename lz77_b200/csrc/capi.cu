@@ -109,6 +109,7 @@ int make_params(int sb, int la, Params *P)
     P->window = sb < cap ? sb : cap;
     P->block = lz77_gpu_block_size(sb);
     P->block_shift = bitof((int)P->block);
+    P->tile_shift = P->block_shift < 17 ? P->block_shift : 17;
     return LZ77_OK;
 }
 
@@ -141,7 +142,7 @@ long lz77_gpu_encode_bound(long n_in, int sb, int la)
 long lz77_gpu_block_size(int sb)
 {
     if (sb == -1) sb = LZ77_DEFAULT_SB;
-    return sb <= 8191 ? 65536L : 131072L;
+    return sb <= 8191 ? 65536L : 262144L;
 }
 
 long lz77_gpu_segment_size(void) { return kSegBytes; }
@@ -455,7 +456,8 @@ int read_header(const unsigned char hdr[4], long n_in, Params *P, long long *n_t
 }
 
 // runs pass 1; on success *n_out is the decoded size
-int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_tokens, long *n_out)
+int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_tokens, long *n_out,
+                       bool *cross_block)
 {
     if (!g.ready) return LZ77_E_NODEVICE;
     if (n_in < 0 || !d_in || !n_out) return LZ77_E_ARG;
@@ -485,6 +487,7 @@ int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_toke
     CK(cudaStreamSynchronize(g.stream));
     const DecodeInfo *info = (const DecodeInfo *)g.pinned;
     *n_out = (long)info->n_out;
+    if (cross_block) *cross_block = info->cross_block != 0;
     g.last.launches = decode_launch_count(false);
     if (g.timing) g.last.dec_scan_ms = ms_between(g.ev[0], g.ev[1]);
     return LZ77_OK;
@@ -514,7 +517,7 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
         *n_out = 0;
         return LZ77_OK;
     }
-    const long long tile_bytes = 1LL << P.block_shift;
+    const long long tile_bytes = 1LL << P.tile_shift;
     long long max_out = K << P.lb;  // len + 1 <= 2^lb
     if (max_out > out_cap) max_out = out_cap;
     const size_t o_cap = (((size_t)max_out + tile_bytes) + 15) & ~(size_t)15;
@@ -574,22 +577,22 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
                 result = LZ77_E_SPACE;
                 break;
             }
-            tile_end = (pos + tile_bytes - 1) >> P.block_shift;
+            tile_end = (pos + tile_bytes - 1) >> P.tile_shift;
         } else {
-            tile_end = pos > 0 ? (pos - 1) >> P.block_shift : 0;  // tiles wholly scanned
-            const long long cap_tiles = (long long)(max_out >> P.block_shift);
+            tile_end = pos > 0 ? (pos - 1) >> P.tile_shift : 0;  // tiles wholly scanned
+            const long long cap_tiles = (long long)(max_out >> P.tile_shift);
             if (tile_end > cap_tiles) tile_end = cap_tiles;        // never past the caller's buffer
             if (tile_end < tiles_done) tile_end = tiles_done;
         }
         if (tile_end > tiles_done) {
             CK(cudaStreamWaitEvent(g.aux, ev_scan[c], 0));
             CK(launch_decode_tiles_range((const uint32_t *)g.stage_in, n_in, K, tiles_done,
-                                         tile_end, last, pos, (int)c, P, g.scratch,
+                                         tile_end, last, pos, (int)c, false, P, g.scratch,
                                          (uint8_t *)g.stage_out, g.aux));
             CK(cudaEventRecord(ev_tiles[c], g.aux));
             CK(cudaStreamWaitEvent(g.copy_out, ev_tiles[c], 0));
-            const long long b_lo = tiles_done << P.block_shift;
-            long long b_hi = tile_end << P.block_shift;
+            const long long b_lo = tiles_done << P.tile_shift;
+            long long b_hi = tile_end << P.tile_shift;
             if (last && b_hi > pos) b_hi = pos;
             CK(cudaMemcpyAsync(out + b_lo, (char *)g.stage_out + b_lo, (size_t)(b_hi - b_lo),
                                cudaMemcpyDeviceToHost, g.copy_out));
@@ -615,7 +618,7 @@ int lz77_gpu_decode_size_device(const void *d_in, long n_in, long *n_out)
 {
     Params P;
     long long k = 0;
-    return decode_scan_device(d_in, n_in, &P, &k, n_out);
+    return decode_scan_device(d_in, n_in, &P, &k, n_out, nullptr);
 }
 
 int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_cap, long *n_out)
@@ -623,15 +626,16 @@ int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_ca
     Params P;
     long long k = 0;
     long n = 0;
-    int rc = decode_scan_device(d_in, n_in, &P, &k, &n);
+    bool cross = false;
+    int rc = decode_scan_device(d_in, n_in, &P, &k, &n, &cross);
     if (rc) return rc;
     *n_out = n;
     if (n == 0) return LZ77_OK;
     if (!d_out || (((uintptr_t)d_out) & 15)) return LZ77_E_ARG;
     if (out_cap < n) return LZ77_E_SPACE;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
-    CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, P, g.scratch, (uint8_t *)d_out,
-                          g.stream));
+    CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, cross, P, g.scratch,
+                          (uint8_t *)d_out, g.stream));
     if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
     // the error flag is final only after pass 2
     DecodeInfo *d_info = (DecodeInfo *)g.scratch;
@@ -685,7 +689,8 @@ int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long
     Params P;
     long long k = 0;
     long n = 0;
-    rc = decode_scan_device(g.stage_in, n_in, &P, &k, &n);
+    bool cross = false;
+    rc = decode_scan_device(g.stage_in, n_in, &P, &k, &n, &cross);
     if (rc) return rc;
     const float scan_ms = g.last.dec_scan_ms;
     *n_out = n;
@@ -695,7 +700,7 @@ int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long
     rc = grow(&g.stage_out, &g.stage_out_cap, (((size_t)n + 15) & ~(size_t)15) + 16);
     if (rc) return rc;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
-    CK(launch_decode_copy((const uint32_t *)g.stage_in, n_in, k, n, P, g.scratch,
+    CK(launch_decode_copy((const uint32_t *)g.stage_in, n_in, k, n, cross, P, g.scratch,
                           (uint8_t *)g.stage_out, g.stream));
     if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
     CK(cudaMemcpyAsync(g.pinned, g.scratch, sizeof(DecodeInfo), cudaMemcpyDeviceToHost, g.stream));

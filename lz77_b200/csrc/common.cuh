@@ -24,6 +24,8 @@ struct Params {
     int window;        // usable search reach: min(sb, 2^ob - 1)  (Appendix B2)
     long long block;   // independent block size in bytes (power of two)
     int block_shift;
+    int tile_shift;    // decode tile = min(block, 128 KiB): what fits shared memory (a
+                       // 256 KiB block is decoded as two tiles)
 };
 
 __host__ __device__ inline int bitof(int n)  // bitio.c:41-43 in integers

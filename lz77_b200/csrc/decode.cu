@@ -91,17 +91,17 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
 
     // per lane: inclusive scan of len+1 over this warp's 512 tokens
     uint32_t incl[kDsRows];
-    uint32_t L[kDsRows];
+    uint32_t TOK[kDsRows];  // the token itself (len and off are re-extracted below)
     uint32_t carry = 0;
 #pragma unroll
     for (int r = 0; r < kDsRows; r++) {
         const long long k = warp_base + r * 32 + lane;
-        uint32_t l1 = 0;
+        uint32_t l1 = 0, tok = 0;
         if (k < n_tokens) {
-            const uint32_t tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
+            tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
             l1 = ((tok >> P.ob) & len_mask) + 1u;
         }
-        L[r] = l1;
+        TOK[r] = tok;
         uint32_t x = l1;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -158,20 +158,26 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
     for (int r = 0; r < kDsRows; r++) {
         const long long k = warp_base + r * 32 + lane;
         if (k >= n_tokens) continue;
-        const long long pos = (long long)(base_pos + incl[r] - L[r]);
+        const uint32_t len = (TOK[r] >> P.ob) & len_mask;
+        const uint32_t Lr = len + 1u;
+        const long long pos = (long long)(base_pos + incl[r] - Lr);
         // low 32 bits of the output position of tokens 32g .. 32g+31 (the tile
         // kernel only needs positions relative to its tile)
         if (lane == 0) group_pos[k >> 5] = (uint32_t)pos;
+        // a source before the start of the token's block: not a stream of the
+        // block-parallel encoder (then the tiles of a block pair must run in order)
+        if (len > 0 && (long long)(TOK[r] & ((1u << P.ob) - 1u)) > (pos & (P.block - 1)))
+            info->cross_block = 1u;
         const long long j = (pos + tile_bytes - 1) >> tile_shift;
-        if ((j << tile_shift) < pos + (long long)L[r]) {
+        if ((j << tile_shift) < pos + (long long)Lr) {
             tile_tok[j] = k;
             tile_pos[j] = pos;
         }
         if (k == n_tokens - 1) {
-            info->n_out = (unsigned long long)(pos + L[r]);
+            info->n_out = (unsigned long long)(pos + Lr);
             if (host_n_out) {  // read by the chunked host path without a D2H memcpy
                 *reinterpret_cast<volatile unsigned long long *>(host_n_out) =
-                    (unsigned long long)(pos + L[r]);
+                    (unsigned long long)(pos + Lr);
                 __threadfence_system();
             }
         }
@@ -230,7 +236,8 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                         const long long *__restrict__ tile_pos,
                         const uint32_t *__restrict__ group_pos, long long tile_begin,
                         long long tile_end, long long n_tiles, long long n_out, uint8_t *out,
-                        unsigned int *tile_done, unsigned int *ticket, DecodeInfo *info)
+                        unsigned int *tile_done, unsigned int *ticket, DecodeInfo *info,
+                        int pair_mode)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int kWarps = kThreads / 32;
@@ -249,7 +256,14 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
 
     while (true) {
         if (threadIdx.x == 0) {
-            s_tile = tile_begin + atomicAdd(ticket, 1u);  // tiles start in order
+            long long t = atomicAdd(ticket, 1u);  // tiles start in ticket order
+            if (pair_mode) {
+                // a 256 KiB block is two tiles and the second may copy from the first:
+                // hand out all first halves, then all second halves, so nobody waits
+                const long long n_even = (tile_end - tile_begin + 1) >> 1;
+                t = t < n_even ? 2 * t : 2 * (t - n_even) + 1;
+            }
+            s_tile = tile_begin + t;
             s_next_group = 0;
         }
         __syncthreads();
@@ -419,14 +433,14 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
 
 int decode_tile_bytes(const Params &P)
 {
-    return (int)P.block;  // tile == encoder block: its own streams never leave a tile
+    return 1 << P.tile_shift;  // the encoder block, or half of a 256 KiB block
 }
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 static DecodeScratch carve_decode(void *scratch, long long n_tokens, const Params &P)
 {
-    const int tile_shift = P.block_shift;
+    const int tile_shift = P.tile_shift;
     const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
     const long long max_out = n_tokens << P.lb;  // len + 1 <= 2^lb
     const long long max_tiles = (max_out >> tile_shift) + 2;
@@ -453,7 +467,7 @@ static DecodeScratch carve_decode(void *scratch, long long n_tokens, const Param
 size_t decode_scratch_bytes(long long n_tokens, const Params &P)
 {
     const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
-    const long long max_tiles = ((n_tokens << P.lb) >> P.block_shift) + 2;
+    const long long max_tiles = ((n_tokens << P.lb) >> P.tile_shift) + 2;
     return 512 + al256((size_t)n_chunks * 8) + al256((size_t)max_tiles * 4) +
            2 * al256((size_t)max_tiles * 8) + al256((size_t)((n_tokens + 31) / 32) * 4) + 1024;
 }
@@ -479,7 +493,7 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
     const long long n_words = (n_in_bytes + 3) / 4;
     if (n_chunks > 0)
         lz77_decode_scan_kernel<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(
-            d_in_words, n_words, tok_end, P, P.block_shift, s.status, s.tile_tok, s.tile_pos,
+            d_in_words, n_words, tok_end, P, P.tile_shift, s.status, s.tile_tok, s.tile_pos,
             s.group_pos, s.tickets, s.info, host_n_out);
     return cudaGetLastError();
 }
@@ -501,11 +515,11 @@ cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
 cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in_bytes,
                                       long long n_tokens, long long tile_begin,
                                       long long tile_end, bool last, long long n_out,
-                                      int launch_idx, const Params &P, void *scratch,
-                                      uint8_t *d_out, cudaStream_t st)
+                                      int launch_idx, bool pair_mode, const Params &P,
+                                      void *scratch, uint8_t *d_out, cudaStream_t st)
 {
     DecodeScratch s = carve_decode(scratch, n_tokens, P);
-    const int tile_shift = P.block_shift;
+    const int tile_shift = P.tile_shift;
     const long long tile_bytes = 1LL << tile_shift;
     const long long n_words = (n_in_bytes + 3) / 4;
     const long long n_run = tile_end - tile_begin;
@@ -530,7 +544,7 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
                                                  s.tile_tok, s.tile_pos, s.group_pos, tile_begin,
                                                  tile_end,
                                                  n_tiles_total, n_out_eff, d_out, s.tile_done,
-                                                 ticket, s.info);
+                                                 ticket, s.info, pair_mode ? 1 : 0);
     } else {
         auto kern = lz77_decode_tile_kernel<1024, 1>;
         cudaError_t rc =
@@ -542,19 +556,21 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
                                                   s.tile_tok, s.tile_pos, s.group_pos, tile_begin,
                                                  tile_end,
                                                   n_tiles_total, n_out_eff, d_out, s.tile_done,
-                                                  ticket, s.info);
+                                                  ticket, s.info, pair_mode ? 1 : 0);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
-                               long long n_tokens, long long n_out, const Params &P,
-                               void *scratch, uint8_t *d_out, cudaStream_t st)
+                               long long n_tokens, long long n_out, bool cross_block,
+                               const Params &P, void *scratch, uint8_t *d_out, cudaStream_t st)
 {
-    const long long tile_bytes = 1LL << P.block_shift;
-    const long long n_tiles = (n_out + tile_bytes - 1) >> P.block_shift;
+    // tiles in pairs only for streams whose matches stay inside their 256 KiB block
+    const bool pair_mode = P.block_shift > P.tile_shift && !cross_block;
+    const long long tile_bytes = 1LL << P.tile_shift;
+    const long long n_tiles = (n_out + tile_bytes - 1) >> P.tile_shift;
     return launch_decode_tiles_range(d_in_words, n_in_bytes, n_tokens, 0, n_tiles, true, n_out, 0,
-                                     P, scratch, d_out, st);
+                                     pair_mode, P, scratch, d_out, st);
 }
 
 }  // namespace lz77

@@ -48,7 +48,8 @@ cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Param
 struct DecodeInfo {            // lives in device scratch, copied back by the C ABI
     unsigned long long n_out;  // decoded size
     unsigned int error;        // != 0: malformed stream (bad offset)
-    unsigned int pad;
+    unsigned int cross_block;  // != 0: a match source lies before its block (not a stream of
+                               // the block-parallel encoder): tiles must run in order
 };
 
 int decode_tile_bytes(const Params &P);
@@ -67,11 +68,11 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
 cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in_bytes,
                                       long long n_tokens, long long tile_begin,
                                       long long tile_end, bool last, long long n_out,
-                                      int launch_idx, const Params &P, void *scratch,
-                                      uint8_t *d_out, cudaStream_t st);
+                                      int launch_idx, bool pair_mode, const Params &P,
+                                      void *scratch, uint8_t *d_out, cudaStream_t st);
 // pass 2: tile decode (needs the decoded size pass 1 produced)
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
-                               long long n_tokens, long long n_out, const Params &P,
-                               void *scratch, uint8_t *d_out, cudaStream_t st);
+                               long long n_tokens, long long n_out, bool cross_block,
+                               const Params &P, void *scratch, uint8_t *d_out, cudaStream_t st);
 
 }  // namespace lz77

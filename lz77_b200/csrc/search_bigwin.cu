@@ -3,10 +3,9 @@
 //
 // The per-tile bucket build of search_bucket.cu does not fit shared memory when
 // the window is 64 KiB, so the buckets are built once per independent block
-// (128 KiB) into HBM / L2 and shared by all the tiles of the block:
+// (256 KiB) into HBM / L2 and shared by all the tiles of the block:
 //
-//   lz77_block_sort_kernel   one CTA per block.  The block is staged into shared
-//       memory with one TMA bulk copy, then its positions are sorted by
+//   lz77_block_sort_kernel   one CTA per block (256 KiB): its positions are sorted by
 //       key = (x[q] & 127) << 6 | x[q+1] & 63 (8192 buckets) with a stable two-pass
 //       LSD radix sort (digit x[q+1]&63, then digit x[q]&127); per-warp digit counters
 //       + MATCH.ANY ranks keep every bucket in ascending position order.
@@ -43,14 +42,16 @@ constexpr int kSortWarps = kSortThreads / 32;
 // per-block stable sort of positions by key
 // ---------------------------------------------------------------------------
 
-// One stable counting-sort pass over n elements.  Element i is src[i] (or i when
-// src == nullptr); its digit comes from digit_of(element).  Warp w handles the
-// contiguous run [w*chunk, (w+1)*chunk) so that equal digits keep their order.
-template <int kBins, typename DigitFn>
-__device__ __forceinline__ void radix_pass(const uint32_t *src, uint32_t *dst, int n,
-                                           uint32_t *cnt /* [kSortWarps][kBins] */,
-                                           uint32_t *bin_start /* [kBins + 1] */,
-                                           uint32_t *s_warp, uint32_t *s_total, DigitFn digit_of)
+constexpr int kPosBits = 18;                     // positions inside a block (<= 256 KiB)
+constexpr uint32_t kPosMask = (1u << kPosBits) - 1u;
+
+// One stable counting-sort pass over n elements.  Element i is elem_of(i); its
+// digit is digit_of(element) and store_of(element) is what lands in dst.  Warp w
+// handles the contiguous run [w*chunk, (w+1)*chunk) so equal digits keep order.
+template <int kBins, typename ElemFn, typename DigitFn, typename StoreFn>
+__device__ __forceinline__ void radix_pass(uint32_t *dst, int n, uint32_t *cnt, uint32_t *bin_start,
+                                           uint32_t *s_warp, uint32_t *s_total, ElemFn elem_of,
+                                           DigitFn digit_of, StoreFn store_of)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -60,10 +61,8 @@ __device__ __forceinline__ void radix_pass(const uint32_t *src, uint32_t *dst, i
 
     for (int i = threadIdx.x; i < kSortWarps * kBins; i += kSortThreads) cnt[i] = 0u;
     __syncthreads();
-    for (int i = cbase + lane; i < cend; i += 32) {
-        const uint32_t el = src ? src[i] : (uint32_t)i;
-        atomicAdd(&cnt[warp * kBins + digit_of(el)], 1u);
-    }
+    for (int i = cbase + lane; i < cend; i += 32)
+        atomicAdd(&cnt[warp * kBins + digit_of(elem_of(i))], 1u);
     __syncthreads();
     // exclusive scan down the warps of every bin, then across the bins
     uint32_t tot = 0;
@@ -76,72 +75,68 @@ __device__ __forceinline__ void radix_pass(const uint32_t *src, uint32_t *dst, i
     }
     const uint32_t base = block_exclusive_scan_u32<kSortThreads>(tot, s_warp, s_total);
     if (threadIdx.x < kBins) bin_start[threadIdx.x] = base;
-    if (threadIdx.x == kBins) bin_start[kBins] = *s_total;
     __syncthreads();
     for (int r = 0; r < rows; r++) {
         const int i = cbase + r * 32 + lane;
         const bool valid = i < cend;
         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
         if (valid) {
-            const uint32_t el = src ? src[i] : (uint32_t)i;
+            const uint32_t el = elem_of(i);
             const int d = digit_of(el);
             const unsigned peers = __match_any_sync(vmask, d);
             const int leader = __ffs(peers) - 1;
             uint32_t old = 0;
             if (lane == leader) old = atomicAdd(&cnt[warp * kBins + d], (uint32_t)__popc(peers));
             old = __shfl_sync(peers, old, leader);
-            dst[bin_start[d] + old + __popc(peers & lt_mask)] = el;
+            dst[bin_start[d] + old + __popc(peers & lt_mask)] = store_of(el);
         }
     }
     __threadfence_block();
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSortThreads, 1)
+// The block is read straight from HBM/L2 (sequentially, once per pass 1): pass 1
+// orders the positions by the low digit x[q+1]&63 and stores them with the high
+// digit x[q]&127 packed above the position, so pass 2 needs no data access.
+__global__ void __launch_bounds__(kSortThreads, 2)
 lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_shift,
                        uint32_t *__restrict__ sorted, uint32_t *__restrict__ tmp,
                        uint32_t *__restrict__ bstart)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
-    __shared__ uint32_t bin_start[257];
+    __shared__ uint32_t bin_start[(1 << kBigB0Bits) + 1];
 
     const long long block_bytes = 1LL << block_shift;
     const long long blk_lo = (long long)blockIdx.x << block_shift;
     const int nb = (int)min(block_bytes, n - blk_lo);
-    uint8_t *data = smem;                                                  // block bytes + pad
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem + block_bytes + 64); // [32][256]
-    uint32_t *cnt2 = cnt + kSortWarps * 256;                               // [8192] bucket sizes
+    const uint8_t *data = in + blk_lo;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);                 // [32 warps][128 bins]
+    uint32_t *cnt2 = cnt + kSortWarps * (1 << kBigB0Bits);              // [8192] bucket sizes
     uint32_t *my_sorted = sorted + blk_lo;
     uint32_t *my_tmp = tmp + blk_lo;
     uint32_t *my_bstart = bstart + (long long)blockIdx.x * (kBigBuckets + 1);
+    // byte q+1 of the last position of the input does not exist: it reads as 0
+    auto byte_at = [&](int q) -> uint32_t { return blk_lo + q < n ? (uint32_t)data[q] : 0u; };
 
-    const int bulk = nb & ~15;
-    if (threadIdx.x == 0) {
-        mbar_init(&mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && bulk > 0) {
-        mbar_expect_tx(&mbar, (uint32_t)bulk);
-        tma_load_1d(data, in + blk_lo, (uint32_t)bulk, &mbar);
-    }
-    for (int i = bulk + threadIdx.x; i < nb + 64; i += kSortThreads)
-        data[i] = i < nb ? in[blk_lo + i] : (uint8_t)0;
     for (int i = threadIdx.x; i < kBigBuckets; i += kSortThreads) cnt2[i] = 0u;
-    if (bulk > 0) mbar_wait(&mbar, 0);
     __syncthreads();
-
     // bucket sizes (for the bucket start table)
     for (int i = threadIdx.x; i < nb; i += kSortThreads)
-        atomicAdd(&cnt2[big_key(data[i], data[i + 1])], 1u);
-    // pass 1: low digit = x[q+1] & 31 ; pass 2: high digit = x[q]
-    radix_pass<1 << kBigB1Bits>(nullptr, my_tmp, nb, cnt, bin_start, s_warp, &s_total,
-                                [&](uint32_t q) { return (int)(data[q + 1] & ((1u << kBigB1Bits) - 1u)); });
-    radix_pass<1 << kBigB0Bits>(my_tmp, my_sorted, nb, cnt, bin_start, s_warp, &s_total,
-                                [&](uint32_t q) { return (int)(data[q] & ((1u << kBigB0Bits) - 1u)); });
+        atomicAdd(&cnt2[big_key(byte_at(i), byte_at(i + 1))], 1u);
+    // pass 1: low digit = x[q+1] & 63, entries leave as q | (x[q] & 127) << 18
+    radix_pass<1 << kBigB1Bits>(
+        my_tmp, nb, cnt, bin_start, s_warp, &s_total,
+        [&](int i) { return (uint32_t)i; },
+        [&](uint32_t q) { return (int)(byte_at((int)q + 1) & ((1u << kBigB1Bits) - 1u)); },
+        [&](uint32_t q) { return q | ((byte_at((int)q) & ((1u << kBigB0Bits) - 1u)) << kPosBits); });
+    // pass 2: high digit, carried in the entry
+    radix_pass<1 << kBigB0Bits>(
+        my_sorted, nb, cnt, bin_start, s_warp, &s_total,
+        [&](int i) { return my_tmp[i]; },
+        [&](uint32_t el) { return (int)(el >> kPosBits); },
+        [&](uint32_t el) { return el & kPosMask; });
     // bucket starts: exclusive scan of the 8192 bucket sizes
     {
         constexpr int per = kBigBuckets / kSortThreads;  // 8
@@ -360,8 +355,7 @@ cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Param
     uint32_t *bstart = tmp + npos;
 
     {
-        const size_t smem = (size_t)P.block + 64 + (size_t)kSortWarps * 256 * 4 +
-                            (size_t)kBigBuckets * 4;
+        const size_t smem = (size_t)kSortWarps * (1 << kBigB0Bits) * 4 + (size_t)kBigBuckets * 4;
         cudaError_t rc = cudaFuncSetAttribute(
             lz77_block_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (rc != cudaSuccess) return rc;

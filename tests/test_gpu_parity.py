@@ -382,12 +382,13 @@ def test_device_buffers_must_be_aligned(lz):
 
 
 @pytest.mark.parametrize("kind,sb,la,tol", [("zipf_text", 4095, 15, 0.02), ("log_like", 4095, 15, 0.02),
-                                            ("random", 4095, 15, 0.02), ("zipf_text", 65535, 255, 0.10)])
+                                            ("random", 4095, 15, 0.02), ("zipf_text", 65535, 255, 0.05),
+                                            ("random", 65535, 255, 0.035)])
 def test_compressed_size_close_to_reference(lz, orc, kind, sb, la, tol):
-    """Block cuts (64 / 128 KiB) and parse restarts (1 KiB) are the only reasons the
+    """Block cuts (64 / 256 KiB) and parse restarts (1 KiB) are the only reasons the
     stream is longer than the reference's: within 2 % at the default parameters,
-    10 % at the 64 KiB window, where a 128 KiB block starts with an empty window
-    (measured 8.3 % on text; DESIGN.md sections 2 and 9)."""
+    5 % at the 64 KiB window, where every 256 KiB block starts with an empty window
+    (measured 4.2 % on text, 2.9 % on random data; DESIGN.md sections 2 and 9)."""
     from lz77_b200 import synth
     data = synth.make(kind, 3 << 20, seed=61).numpy().tobytes()
     ours = len(lz.encode(data, la=la, sb=sb))
