@@ -142,7 +142,7 @@ long lz77_gpu_encode_bound(long n_in, int sb, int la)
 long lz77_gpu_block_size(int sb)
 {
     if (sb == -1) sb = LZ77_DEFAULT_SB;
-    return sb <= 8191 ? 65536L : 262144L;
+    return sb <= 8191 ? 65536L : 524288L;
 }
 
 long lz77_gpu_segment_size(void) { return kSegBytes; }
@@ -587,7 +587,7 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
         if (tile_end > tiles_done) {
             CK(cudaStreamWaitEvent(g.aux, ev_scan[c], 0));
             CK(launch_decode_tiles_range((const uint32_t *)g.stage_in, n_in, K, tiles_done,
-                                         tile_end, last, pos, (int)c, false, P, g.scratch,
+                                         tile_end, last, pos, (int)c, 0, P, g.scratch,
                                          (uint8_t *)g.stage_out, g.aux));
             CK(cudaEventRecord(ev_tiles[c], g.aux));
             CK(cudaStreamWaitEvent(g.copy_out, ev_tiles[c], 0));

@@ -258,10 +258,21 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
         if (threadIdx.x == 0) {
             long long t = atomicAdd(ticket, 1u);  // tiles start in ticket order
             if (pair_mode) {
-                // a 256 KiB block is two tiles and the second may copy from the first:
-                // hand out all first halves, then all second halves, so nobody waits
-                const long long n_even = (tile_end - tile_begin + 1) >> 1;
-                t = t < n_even ? 2 * t : 2 * (t - n_even) + 1;
+                // a large block is 2^pair_mode tiles and a tile may copy from the tiles of
+                // its block before it: hand out the first tile of every block, then the
+                // second of every block, ... so no CTA ever waits for a tile of its block
+                const long long n = tile_end - tile_begin;
+                const int tpb = 1 << pair_mode;
+                long long tile = n;
+                for (int p = 0; p < tpb; p++) {
+                    const long long cnt = n > p ? (n - p + tpb - 1) >> pair_mode : 0;
+                    if (t < cnt) {
+                        tile = p + (t << pair_mode);
+                        break;
+                    }
+                    t -= cnt;
+                }
+                t = tile;
             }
             s_tile = tile_begin + t;
             s_next_group = 0;
@@ -515,7 +526,7 @@ cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
 cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in_bytes,
                                       long long n_tokens, long long tile_begin,
                                       long long tile_end, bool last, long long n_out,
-                                      int launch_idx, bool pair_mode, const Params &P,
+                                      int launch_idx, int pair_mode, const Params &P,
                                       void *scratch, uint8_t *d_out, cudaStream_t st)
 {
     DecodeScratch s = carve_decode(scratch, n_tokens, P);
@@ -544,7 +555,7 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
                                                  s.tile_tok, s.tile_pos, s.group_pos, tile_begin,
                                                  tile_end,
                                                  n_tiles_total, n_out_eff, d_out, s.tile_done,
-                                                 ticket, s.info, pair_mode ? 1 : 0);
+                                                 ticket, s.info, pair_mode);
     } else {
         auto kern = lz77_decode_tile_kernel<1024, 1>;
         cudaError_t rc =
@@ -556,7 +567,7 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
                                                   s.tile_tok, s.tile_pos, s.group_pos, tile_begin,
                                                  tile_end,
                                                   n_tiles_total, n_out_eff, d_out, s.tile_done,
-                                                  ticket, s.info, pair_mode ? 1 : 0);
+                                                  ticket, s.info, pair_mode);
     }
     return cudaGetLastError();
 }
@@ -565,8 +576,9 @@ cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, long long n_out, bool cross_block,
                                const Params &P, void *scratch, uint8_t *d_out, cudaStream_t st)
 {
-    // tiles in pairs only for streams whose matches stay inside their 256 KiB block
-    const bool pair_mode = P.block_shift > P.tile_shift && !cross_block;
+    // phase order only for streams whose matches stay inside their (multi-tile) block
+    const int pair_mode = (P.block_shift > P.tile_shift && !cross_block)
+                              ? P.block_shift - P.tile_shift : 0;
     const long long tile_bytes = 1LL << P.tile_shift;
     const long long n_tiles = (n_out + tile_bytes - 1) >> P.tile_shift;
     return launch_decode_tiles_range(d_in_words, n_in_bytes, n_tokens, 0, n_tiles, true, n_out, 0,

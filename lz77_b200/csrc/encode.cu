@@ -404,7 +404,7 @@ EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P)
 }
 
 // chunks of a chunked encode must start on a block boundary (the largest block size)
-long long encode_chunk_granule() { return 262144; }
+long long encode_chunk_granule() { return 524288; }
 
 // Encodes input bytes [lo, lo + n_chunk) (lo a multiple of encode_chunk_granule(),
 // hence of the block size; the scans of successive chunks run in stream order, so a

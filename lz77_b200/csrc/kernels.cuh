@@ -68,7 +68,7 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
 cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in_bytes,
                                       long long n_tokens, long long tile_begin,
                                       long long tile_end, bool last, long long n_out,
-                                      int launch_idx, bool pair_mode, const Params &P,
+                                      int launch_idx, int pair_mode, const Params &P,
                                       void *scratch, uint8_t *d_out, cudaStream_t st);
 // pass 2: tile decode (needs the decoded size pass 1 produced)
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,

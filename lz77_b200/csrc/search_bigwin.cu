@@ -3,9 +3,9 @@
 //
 // The per-tile bucket build of search_bucket.cu does not fit shared memory when
 // the window is 64 KiB, so the buckets are built once per independent block
-// (256 KiB) into HBM / L2 and shared by all the tiles of the block:
+// (512 KiB) into HBM / L2 and shared by all the tiles of the block:
 //
-//   lz77_block_sort_kernel   one CTA per block (256 KiB): its positions are sorted by
+//   lz77_block_sort_kernel   one CTA per block (512 KiB): its positions are sorted by
 //       key = (x[q] & 127) << 6 | x[q+1] & 63 (8192 buckets) with a stable two-pass
 //       LSD radix sort (digit x[q+1]&63, then digit x[q]&127); per-warp digit counters
 //       + MATCH.ANY ranks keep every bucket in ascending position order.
@@ -42,7 +42,7 @@ constexpr int kSortWarps = kSortThreads / 32;
 // per-block stable sort of positions by key
 // ---------------------------------------------------------------------------
 
-constexpr int kPosBits = 18;                     // positions inside a block (<= 256 KiB)
+constexpr int kPosBits = 19;                     // positions inside a block (<= 512 KiB)
 constexpr uint32_t kPosMask = (1u << kPosBits) - 1u;
 
 // One stable counting-sort pass over n elements.  Element i is elem_of(i); its
@@ -125,7 +125,7 @@ lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_sh
     // bucket sizes (for the bucket start table)
     for (int i = threadIdx.x; i < nb; i += kSortThreads)
         atomicAdd(&cnt2[big_key(byte_at(i), byte_at(i + 1))], 1u);
-    // pass 1: low digit = x[q+1] & 63, entries leave as q | (x[q] & 127) << 18
+    // pass 1: low digit = x[q+1] & 63, entries leave as q | (x[q] & 127) << 19
     radix_pass<1 << kBigB1Bits>(
         my_tmp, nb, cnt, bin_start, s_warp, &s_total,
         [&](int i) { return (uint32_t)i; },

@@ -51,7 +51,7 @@ def test_format_arithmetic_matches_oracle(lib, orc):
             assert lib.lz77_gpu_encode_bound(n, sb, la) == orc.encode_bound(n, sb, la)
     assert lib.lz77_gpu_encode_bound(10, -1, -1) == 4 + 30
     assert lib.lz77_gpu_block_size(4095) == 65536
-    assert lib.lz77_gpu_block_size(65535) == 262144
+    assert lib.lz77_gpu_block_size(65535) == 524288
     seg = lib.lz77_gpu_segment_size()
     assert seg > 0 and 65536 % seg == 0
 
