@@ -34,6 +34,8 @@ struct Context {
     std::vector<cudaEvent_t> pool;      // untimed events of the chunked host paths (reused)
     void *scratch = nullptr;
     size_t scratch_cap = 0;
+    void *jump = nullptr;  // pointer-jumping state of the cross-block decoder
+    size_t jump_cap = 0;
     void *stage_in = nullptr;   // device staging for the host entry points
     size_t stage_in_cap = 0;
     void *stage_out = nullptr;
@@ -165,6 +167,7 @@ void lz77_gpu_shutdown(void)
     for (auto &e : g.ev) cudaEventDestroy(e);
     for (auto &e : g.pool) cudaEventDestroy(e);
     if (g.scratch) cudaFree(g.scratch);
+    if (g.jump) cudaFree(g.jump);
     if (g.stage_in) cudaFree(g.stage_in);
     if (g.stage_out) cudaFree(g.stage_out);
     if (g.pinned) cudaFreeHost(g.pinned);
@@ -564,10 +567,14 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
 
     // as the scans finish: decode the tiles they completed, copy them back
     long long tiles_done = 0, n_total = 0, pos_seen = 0;
+    bool cross = false;  // a match left its block: pointer jumping instead of tiles
     int result = LZ77_OK;
     for (long long c = 0; c < n_chunks; c++) {
         CK(cudaEventSynchronize(ev_scan[c]));
-        if (g.pinned_totals[c] != ~0ull) pos_seen = (long long)g.pinned_totals[c];
+        if (g.pinned_totals[c] != ~0ull) {
+            pos_seen = (long long)(g.pinned_totals[c] & ~(1ull << 63));
+            cross = (g.pinned_totals[c] >> 63) != 0;  // sticky: the flag is never cleared
+        }
         const long long pos = pos_seen;
         const bool last = c + 1 == n_chunks;
         long long tile_end;
@@ -586,9 +593,17 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
         }
         if (tile_end > tiles_done) {
             CK(cudaStreamWaitEvent(g.aux, ev_scan[c], 0));
-            CK(launch_decode_tiles_range((const uint32_t *)g.stage_in, n_in, K, tiles_done,
-                                         tile_end, last, pos, (int)c, 0, P, g.scratch,
-                                         (uint8_t *)g.stage_out, g.aux));
+            if (cross) {
+                if ((rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes()))) return rc;
+                CK(launch_decode_jump_range((const uint32_t *)g.stage_in, n_in, K,
+                                            tiles_done << P.tile_shift,
+                                            last ? pos : tile_end << P.tile_shift, last, P,
+                                            g.scratch, g.jump, (uint8_t *)g.stage_out, g.aux));
+            } else {
+                CK(launch_decode_tiles_range((const uint32_t *)g.stage_in, n_in, K, tiles_done,
+                                             tile_end, last, pos, (int)c, 0, P, g.scratch,
+                                             (uint8_t *)g.stage_out, g.aux));
+            }
             CK(cudaEventRecord(ev_tiles[c], g.aux));
             CK(cudaStreamWaitEvent(g.copy_out, ev_tiles[c], 0));
             const long long b_lo = tiles_done << P.tile_shift;
@@ -633,8 +648,9 @@ int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_ca
     if (n == 0) return LZ77_OK;
     if (!d_out || (((uintptr_t)d_out) & 15)) return LZ77_E_ARG;
     if (out_cap < n) return LZ77_E_SPACE;
+    if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes()))) return rc;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
-    CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, cross, P, g.scratch,
+    CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, cross, P, g.scratch, g.jump,
                           (uint8_t *)d_out, g.stream));
     if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
     // the error flag is final only after pass 2
@@ -699,8 +715,9 @@ int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long
     if (out_cap < n) return LZ77_E_SPACE;
     rc = grow(&g.stage_out, &g.stage_out_cap, (((size_t)n + 15) & ~(size_t)15) + 16);
     if (rc) return rc;
+    if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes()))) return rc;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
-    CK(launch_decode_copy((const uint32_t *)g.stage_in, n_in, k, n, cross, P, g.scratch,
+    CK(launch_decode_copy((const uint32_t *)g.stage_in, n_in, k, n, cross, P, g.scratch, g.jump,
                           (uint8_t *)g.stage_out, g.stream));
     if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
     CK(cudaMemcpyAsync(g.pinned, g.scratch, sizeof(DecodeInfo), cudaMemcpyDeviceToHost, g.stream));

@@ -75,8 +75,7 @@ __global__ void __launch_bounds__(kDsThreads)
 lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, long long n_tokens,
                         Params P, int tile_shift, unsigned long long *status,
                         long long *__restrict__ tile_tok, long long *__restrict__ tile_pos,
-                        uint32_t *__restrict__ group_pos, unsigned int *tickets, DecodeInfo *info,
-                        unsigned long long *host_n_out /* mapped pinned memory, may be null */)
+                        uint32_t *__restrict__ group_pos, unsigned int *tickets, DecodeInfo *info)
 {
     __shared__ long long s_chunk;
     __shared__ unsigned long long s_warp_tot[kDsThreads / 32];
@@ -175,13 +174,18 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
         }
         if (k == n_tokens - 1) {
             info->n_out = (unsigned long long)(pos + Lr);
-            if (host_n_out) {  // read by the chunked host path without a D2H memcpy
-                *reinterpret_cast<volatile unsigned long long *>(host_n_out) =
-                    (unsigned long long)(pos + Lr);
-                __threadfence_system();
-            }
         }
     }
+}
+
+// The chunked host path reads the scan's progress without a D2H memcpy: the output
+// position behind the last scanned token, bit 63 = a match left its block.
+__global__ void lz77_decode_publish_kernel(const DecodeInfo *info,
+                                           unsigned long long *host_slot /* mapped pinned */)
+{
+    *reinterpret_cast<volatile unsigned long long *>(host_slot) =
+        info->n_out | (info->cross_block ? 1ull << 63 : 0ull);
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------
@@ -475,6 +479,12 @@ static DecodeScratch carve_decode(void *scratch, long long n_tokens, const Param
     return s;
 }
 
+DecodeTables decode_tables(void *scratch, long long n_tokens, const Params &P)
+{
+    const DecodeScratch s = carve_decode(scratch, n_tokens, P);
+    return DecodeTables{s.tile_tok, s.tile_pos, s.group_pos, s.info};
+}
+
 size_t decode_scratch_bytes(long long n_tokens, const Params &P)
 {
     const long long n_chunks = (n_tokens + kDsChunk - 1) / kDsChunk;
@@ -505,7 +515,8 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
     if (n_chunks > 0)
         lz77_decode_scan_kernel<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(
             d_in_words, n_words, tok_end, P, P.tile_shift, s.status, s.tile_tok, s.tile_pos,
-            s.group_pos, s.tickets, s.info, host_n_out);
+            s.group_pos, s.tickets, s.info);
+    if (host_n_out) lz77_decode_publish_kernel<<<1, 1, 0, st>>>(s.info, host_n_out);
     return cudaGetLastError();
 }
 
@@ -574,8 +585,14 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
 
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, long long n_out, bool cross_block,
-                               const Params &P, void *scratch, uint8_t *d_out, cudaStream_t st)
+                               const Params &P, void *scratch, void *jump_scratch,
+                               uint8_t *d_out, cudaStream_t st)
 {
+    // matches that leave their block (a stream of the reference encoder): the tiles
+    // would form a chain, resolve the copies by pointer jumping instead
+    if (cross_block)
+        return launch_decode_jump_range(d_in_words, n_in_bytes, n_tokens, 0, n_out, true, P,
+                                        scratch, jump_scratch, d_out, st);
     // phase order only for streams whose matches stay inside their (multi-tile) block
     const int pair_mode = (P.block_shift > P.tile_shift && !cross_block)
                               ? P.block_shift - P.tile_shift : 0;

@@ -356,7 +356,6 @@ lz77_pack_kernel(const uint32_t *__restrict__ tok_tmp, const uint32_t *__restric
 // host-side launchers
 // ---------------------------------------------------------------------------
 
-constexpr long long kBigSuperChunk = 256ll << 20;  // large-window bucket tables cover this much
 
 size_t encode_scratch_bytes(long long n_in, const Params &P)
 {
@@ -369,7 +368,7 @@ size_t encode_scratch_bytes(long long n_in, const Params &P)
     b += (size_t)((n_part + 63) & ~63LL) * sizeof(unsigned long long); // partials
     b += 256;                                                      // grand total
     if (P.window > 8191)                                           // block-level bucket tables
-        b += bigwin_scratch_bytes(n_in < kBigSuperChunk ? n_in : kBigSuperChunk, P);
+        b += bigwin_scratch_bytes(n_in, P);
     return b + 4096;
 }
 
@@ -444,13 +443,9 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
         cudaError_t rc = launch_parse_bucket(d_in, n_chunk, P, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
     } else if (n_tiles > 0 && !kUseExhaustiveScan) {
-        // large windows: block-level buckets (search_bigwin.cu), a bounded range at a time
-        for (long long o = 0; o < n_chunk; o += kBigSuperChunk) {
-            const long long len = n_chunk - o < kBigSuperChunk ? n_chunk - o : kBigSuperChunk;
-            cudaError_t rc =
-                launch_parse_bigwin(d_in + o, len, P, pl.big, tok_tmp + o, seg_ntok + o / kSegBytes, st);
-            if (rc != cudaSuccess) return rc;
-        }
+        // large windows: block-level buckets (search_bigwin.cu)
+        cudaError_t rc = launch_parse_bigwin(d_in, n_chunk, P, pl.big, tok_tmp, seg_ntok, st);
+        if (rc != cudaSuccess) return rc;
     } else if (n_tiles > 0) {
         auto kern = small_la ? lz77_parse_kernel<true> : lz77_parse_kernel<false>;
         cudaError_t rc =

@@ -52,6 +52,15 @@ struct DecodeInfo {            // lives in device scratch, copied back by the C 
                                // the block-parallel encoder): tiles must run in order
 };
 
+// the tables pass 1 leaves in the decode scratch area
+struct DecodeTables {
+    const long long *tile_tok;  // token containing the first byte of tile j
+    const long long *tile_pos;  // output position of that token
+    const uint32_t *group_pos;  // low 32 bits of the output position of token 32g
+    DecodeInfo *info;
+};
+DecodeTables decode_tables(void *scratch, long long n_tokens, const Params &P);
+
 int decode_tile_bytes(const Params &P);
 size_t decode_scratch_bytes(long long n_tokens, const Params &P);
 int decode_launch_count(bool with_copy);
@@ -70,9 +79,16 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
                                       long long tile_end, bool last, long long n_out,
                                       int launch_idx, int pair_mode, const Params &P,
                                       void *scratch, uint8_t *d_out, cudaStream_t st);
-// pass 2: tile decode (needs the decoded size pass 1 produced)
+// pass 2 (needs the decoded size pass 1 produced): tile decode, or pointer jumping
+// (decode_jump.cu; jump_scratch of decode_jump_scratch_bytes()) when cross_block
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, long long n_out, bool cross_block,
-                               const Params &P, void *scratch, uint8_t *d_out, cudaStream_t st);
+                               const Params &P, void *scratch, void *jump_scratch,
+                               uint8_t *d_out, cudaStream_t st);
+size_t decode_jump_scratch_bytes();
+cudaError_t launch_decode_jump_range(const uint32_t *d_in_words, long long n_in_bytes,
+                                     long long n_tokens, long long out_lo, long long out_hi,
+                                     bool to_end, const Params &P, void *scratch,
+                                     void *jump_scratch, uint8_t *d_out, cudaStream_t st);
 
 }  // namespace lz77

@@ -334,45 +334,92 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
 
 // ---------------------------------------------------------------------------
 
-size_t bigwin_scratch_bytes(long long n_in, const Params &P)
+constexpr long long kBigPiece = 64ll << 20;  // bucket tables are built for this much input at a time
+
+static size_t bigwin_piece_scratch(long long n_in, const Params &P)
 {
     const long long n_blocks = (n_in + P.block - 1) >> P.block_shift;
     const long long npos = n_blocks << P.block_shift;
-    return (size_t)npos * 4 * 2 + (size_t)n_blocks * (kBigBuckets + 1) * 4 + 4096;
+    return ((size_t)npos * 4 * 2 + (size_t)n_blocks * (kBigBuckets + 1) * 4 + 4095) & ~(size_t)4095;
 }
 
-// d_in points at a block boundary; the scratch holds the sorted positions, the
-// radix ping buffer and the bucket start tables for [0, n_in).
+// two table sets: piece k+1 is sorted while piece k is parsed
+size_t bigwin_scratch_bytes(long long n_in, const Params &P)
+{
+    return 2 * bigwin_piece_scratch(n_in < kBigPiece ? n_in : kBigPiece, P) + 4096;
+}
+
+namespace {
+struct BigwinStreams {
+    int device = -1;
+    cudaStream_t sort = nullptr;   // high priority: its few CTAs slip in between parse CTAs
+    cudaEvent_t fork = nullptr, sorted[2] = {nullptr, nullptr}, parsed[2] = {nullptr, nullptr};
+};
+BigwinStreams g_bw;
+
+cudaError_t bigwin_streams()
+{
+    int dev = 0;
+    cudaError_t rc = cudaGetDevice(&dev);
+    if (rc != cudaSuccess) return rc;
+    if (g_bw.device == dev) return cudaSuccess;
+    int lo_pri = 0, hi_pri = 0;
+    rc = cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+    if (rc != cudaSuccess) return rc;
+    rc = cudaStreamCreateWithPriority(&g_bw.sort, cudaStreamNonBlocking, hi_pri);
+    if (rc != cudaSuccess) return rc;
+    cudaEventCreateWithFlags(&g_bw.fork, cudaEventDisableTiming);
+    for (int i = 0; i < 2; i++) {
+        cudaEventCreateWithFlags(&g_bw.sorted[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g_bw.parsed[i], cudaEventDisableTiming);
+    }
+    g_bw.device = dev;
+    return cudaGetLastError();
+}
+}  // namespace
+
+// d_in points at a block boundary.  The input is handled in pieces of kBigPiece
+// bytes: the block sort of piece k+1 runs on a high-priority side stream while
+// piece k is parsed on `st` (two sets of tables in the scratch area).
 cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Params &P,
                                 void *scratch, uint32_t *tok_tmp, uint32_t *seg_ntok,
                                 cudaStream_t st)
 {
     if (n_in <= 0) return cudaSuccess;
-    const long long n_blocks = (n_in + P.block - 1) >> P.block_shift;
-    const long long npos = n_blocks << P.block_shift;
-    uint32_t *sorted = (uint32_t *)scratch;
-    uint32_t *tmp = sorted + npos;
-    uint32_t *bstart = tmp + npos;
+    cudaError_t rc = bigwin_streams();
+    if (rc != cudaSuccess) return rc;
+    const size_t piece_scratch = bigwin_piece_scratch(n_in < kBigPiece ? n_in : kBigPiece, P);
+    const size_t sort_smem = (size_t)kSortWarps * (1 << kBigB0Bits) * 4 + (size_t)kBigBuckets * 4;
+    rc = cudaFuncSetAttribute(lz77_block_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)sort_smem);
+    if (rc != cudaSuccess) return rc;
+    const int hist_cap = (P.window + 15) & ~15;
+    const long long tile_bytes = (long long)kBigWarps * kSegBytes;
+    const size_t parse_smem = (size_t)hist_cap + (size_t)tile_bytes + 128;
+    auto parse = P.la <= 16 ? lz77_parse_bigwin_kernel<true> : lz77_parse_bigwin_kernel<false>;
+    rc = cudaFuncSetAttribute(parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)parse_smem);
+    if (rc != cudaSuccess) return rc;
 
-    {
-        const size_t smem = (size_t)kSortWarps * (1 << kBigB0Bits) * 4 + (size_t)kBigBuckets * 4;
-        cudaError_t rc = cudaFuncSetAttribute(
-            lz77_block_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (rc != cudaSuccess) return rc;
-        lz77_block_sort_kernel<<<(unsigned)n_blocks, kSortThreads, smem, st>>>(
-            d_in, n_in, P.block_shift, sorted, tmp, bstart);
-    }
-    {
-        const int hist_cap = (P.window + 15) & ~15;
-        const long long tile_bytes = (long long)kBigWarps * kSegBytes;
-        const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
-        const size_t smem = (size_t)hist_cap + (size_t)tile_bytes + 128;
-        auto kern = P.la <= 16 ? lz77_parse_bigwin_kernel<true> : lz77_parse_bigwin_kernel<false>;
-        cudaError_t rc =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (rc != cudaSuccess) return rc;
-        kern<<<(unsigned)n_tiles, kBigWarps * 32, smem, st>>>(d_in, n_in, P, hist_cap, sorted,
-                                                              bstart, tok_tmp, seg_ntok);
+    cudaEventRecord(g_bw.fork, st);
+    cudaStreamWaitEvent(g_bw.sort, g_bw.fork, 0);
+    long long k = 0;
+    for (long long o = 0; o < n_in; o += kBigPiece, k++) {
+        const long long len = n_in - o < kBigPiece ? n_in - o : kBigPiece;
+        const int buf = (int)(k & 1);
+        const long long n_blocks = (len + P.block - 1) >> P.block_shift;
+        const long long npos = n_blocks << P.block_shift;
+        uint32_t *sorted = (uint32_t *)((char *)scratch + buf * piece_scratch);
+        uint32_t *tmp = sorted + npos;
+        uint32_t *bstart = tmp + npos;
+        if (k >= 2) cudaStreamWaitEvent(g_bw.sort, g_bw.parsed[buf], 0);  // tables free again
+        lz77_block_sort_kernel<<<(unsigned)n_blocks, kSortThreads, sort_smem, g_bw.sort>>>(
+            d_in + o, len, P.block_shift, sorted, tmp, bstart);
+        cudaEventRecord(g_bw.sorted[buf], g_bw.sort);
+        cudaStreamWaitEvent(st, g_bw.sorted[buf], 0);
+        const long long n_tiles = (len + tile_bytes - 1) / tile_bytes;
+        parse<<<(unsigned)n_tiles, kBigWarps * 32, parse_smem, st>>>(
+            d_in + o, len, P, hist_cap, sorted, bstart, tok_tmp + o, seg_ntok + o / kSegBytes);
+        cudaEventRecord(g_bw.parsed[buf], st);
     }
     return cudaGetLastError();
 }

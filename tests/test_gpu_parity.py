@@ -411,3 +411,101 @@ def test_host_pipeline_chunk_seams(lz, sb, la, n):
     enc = lz.encode(host, la=la, sb=sb)
     assert enc == dev_stream.cpu().numpy().tobytes()
     assert lz.decode(enc) == host.tobytes()
+
+
+# ---- unblocked streams at scale: synthetic token sequences ---------------------
+# Any token sequence whose offsets stay inside the output written so far is a valid
+# stream (lz77.c:164-195), so large unblocked streams need no slow CPU encoder: the
+# tokens are drawn at random and the expected plaintext comes from the oracle decoder.
+
+def _pack_tokens(off, length, lit, sb, la):
+    ob = int(np.ceil(np.log2(sb))) if sb > 1 else 0  # bitof(), bitio.c:41-43
+    lb = int(np.ceil(np.log2(la)))
+    T = ob + lb + 8
+    tok = off.astype(np.uint64) | (length.astype(np.uint64) << np.uint64(ob)) | \
+        (lit.astype(np.uint64) << np.uint64(ob + lb))
+    if T % 8 == 0:
+        payload = tok.astype("<u8").view(np.uint8).reshape(-1, 8)[:, :T // 8].reshape(-1)
+    else:
+        bits = ((tok[:, None] >> np.arange(T, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8)
+        payload = np.packbits(bits.reshape(-1), bitorder="little")
+    hdr = np.array([sb & 255, sb >> 8, la & 255, la >> 8], dtype=np.uint8)
+    return np.concatenate([hdr, payload]).tobytes()
+
+
+def _random_tokens(rng, k, sb, la, far=0.5):
+    length = rng.integers(0, la, size=k, dtype=np.int64)
+    length[0] = 0
+    pos = np.concatenate([[0], np.cumsum(length + 1)[:-1]])
+    reach = np.minimum(pos, sb)
+    # a mix of near offsets (self-overlapping copies) and offsets across the whole window
+    near = rng.integers(1, 9, size=k)
+    wide = 1 + (rng.random(k) * reach).astype(np.int64)
+    off = np.where(rng.random(k) < far, wide, near)
+    off = np.clip(off, 1, np.maximum(reach, 1))
+    off[length == 0] = 0
+    length[reach == 0] = 0
+    off[reach == 0] = 0
+    lit = rng.integers(0, 256, size=k, dtype=np.int64)
+    return off, length, lit
+
+
+@pytest.mark.parametrize("sb,la,k", [(4095, 15, 5_000_000), (65535, 255, 400_000),
+                                     (1000, 20, 600_000), (4095, 15, 40)])
+def test_decode_unblocked_synthetic_tokens(lz, orc, sb, la, k):
+    """Random token sequences whose matches reach back across every tile and piece
+    boundary (the pointer-jumping decoder, several pieces of output)."""
+    rng = np.random.default_rng(k + sb)
+    stream = _pack_tokens(*_random_tokens(rng, k, sb, la), sb, la)
+    want = orc.decode(stream)
+    assert lz.decode_size(stream) == len(want)
+    assert lz.decode(stream) == want
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (65535, 255)])
+def test_decode_unblocked_deep_chains(lz, orc, sb, la):
+    """Worst-case dependency depth: one literal followed by maximum-length copies at
+    offset 1 (every byte depends on its predecessor, depth = output size), then copies
+    at offset SB and at offset 3 (self-overlapping)."""
+    k = 1_600_000 if la == 15 else 120_000
+    length = np.full(k, la - 1, dtype=np.int64)
+    length[:4] = 0
+    off = np.ones(k, dtype=np.int64)
+    off[:4] = 0
+    third = k // 3
+    pos = np.concatenate([[0], np.cumsum(length + 1)[:-1]])
+    off[third:2 * third] = np.minimum(sb, pos[third:2 * third])
+    off[2 * third:] = 3
+    lit = (np.arange(k) * 7 % 251).astype(np.int64)
+    stream = _pack_tokens(off, length, lit, sb, la)
+    want = orc.decode(stream)
+    assert len(want) > (20 << 20)
+    assert lz.decode(stream) == want
+
+
+def test_decode_unblocked_after_blocked_prefix_pipelined(lz, orc):
+    """Host pipeline, 1 MiB chunks: a stream that starts with tokens of the block
+    encoder (decoded tile by tile) and continues with unblocked tokens (pointer
+    jumping from the chunk in which the first such token is seen)."""
+    from lz77_b200 import api, synth
+    sb, la = 4095, 15
+    data = synth.zipf_text(6 << 20, seed=77).numpy().tobytes()
+    head = lz.encode(data, la=la, sb=sb)
+    assert (len(head) - 4) % 3 == 0
+    rng = np.random.default_rng(5)
+    off, length, lit = _random_tokens(rng, 1_500_000, sb, la)
+    # the tail's offsets are valid as they are: 6 MiB of output precede them
+    off = np.where(length > 0, np.maximum(off, 1), 0)
+    off[(length > 0) & (rng.random(len(off)) < 0.3)] = sb
+    tail = _pack_tokens(off, length, lit, sb, la)[4:]
+    stream = head + tail
+    want = orc.decode(stream)
+    assert want[:len(data)] == data and len(want) > len(data) + (8 << 20)
+    api.set_host_chunk(1 << 20)
+    try:
+        assert lz.decode(stream) == want
+    finally:
+        api.set_host_chunk(16 << 20)
+    import torch
+    s = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
+    assert api.decode_tensor(s).cpu().numpy().tobytes() == want
