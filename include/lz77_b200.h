@@ -113,6 +113,19 @@ int lz77_gpu_decode_size_device(const void *d_in, long n_in, long *n_out);
 int lz77_gpu_decode_device(const void *d_in, long n_in,
                            void *d_out, long out_cap, long *n_out);
 
+/* ---- token-array helpers for sharding one stream across GPUs --------------
+ * Tokens are fixed width, so a stream splits at any token without parsing
+ * (the decoder's counterpart of lz77.c:260-283 reading one token at bit
+ * 32 + k*T).  slice_tokens writes a standalone stream: the header of d_in and
+ * tokens [tok_lo, tok_hi) (out_cap a multiple of 4 >= 4 + ceil((hi-lo)*T/8)
+ * rounded up to 4).  token_at returns the token that holds decoded byte `pos`
+ * (the token that starts there when one does) and the decoded position of its
+ * first byte; pos == decoded size gives (token count, decoded size). */
+int lz77_gpu_slice_tokens_device(const void *d_in, long n_in, long tok_lo, long tok_hi,
+                                 void *d_out, long out_cap, long *n_out);
+int lz77_gpu_token_at_device(const void *d_in, long n_in, long pos,
+                             long *tok, long *tok_pos);
+
 /* ---- measurement ---------------------------------------------------------
  * Device time (CUDA events on the library's stream) of each kernel of the
  * last encode / decode call, in milliseconds, and how many kernels ran. */

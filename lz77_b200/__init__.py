@@ -16,6 +16,8 @@ from .api import (  # noqa: F401
     decode_size,
     decode_size_tensor,
     decode_tensor,
+    slice_tokens_tensor,
+    token_at_tensor,
     encode,
     encode_bound,
     encode_tensor,

@@ -28,6 +28,7 @@ EXPORTS = (
     "lz77_gpu_encode", "lz77_gpu_decode_size", "lz77_gpu_decode", "lz77_gpu_encode_device",
     "lz77_gpu_decode_size_device", "lz77_gpu_decode_device", "lz77_gpu_last_timing",
     "lz77_gpu_set_timing", "lz77_gpu_set_stream", "lz77_gpu_set_host_chunk",
+    "lz77_gpu_slice_tokens_device", "lz77_gpu_token_at_device",
 )
 
 
@@ -88,6 +89,8 @@ def load_library() -> C.CDLL:
         "lz77_gpu_set_timing": (None, [ip]),
         "lz77_gpu_set_stream": (ip, [vp]),
         "lz77_gpu_set_host_chunk": (None, [lp]),
+        "lz77_gpu_slice_tokens_device": (ip, [vp, lp, lp, lp, vp, lp, plong]),
+        "lz77_gpu_token_at_device": (ip, [vp, lp, lp, plong, plong]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -301,6 +304,34 @@ def decode_size_tensor(stream) -> int:
     _check(load_library().lz77_gpu_decode_size_device(stream.data_ptr(), stream.numel(),
                                                       C.byref(n)))
     return n.value
+
+
+def slice_tokens_tensor(stream, tok_lo: int, tok_hi: int):
+    """Standalone stream (CUDA uint8 tensor) holding tokens [tok_lo, tok_hi) of `stream`."""
+    import torch
+    assert stream.is_cuda and stream.dtype == torch.uint8 and stream.is_contiguous()
+    init(stream.device.index)
+    torch.cuda.current_stream(stream.device).synchronize()
+    hdr = bytes(stream[:4].cpu().numpy())
+    T = token_bits(hdr[0] | hdr[1] << 8, hdr[2] | hdr[3] << 8)
+    cap = _round16(4 + ((tok_hi - tok_lo) * T + 7) // 8 + 4)
+    out = torch.empty(cap, dtype=torch.uint8, device=stream.device)
+    n = C.c_long(0)
+    _check(load_library().lz77_gpu_slice_tokens_device(stream.data_ptr(), stream.numel(), tok_lo,
+                                                       tok_hi, out.data_ptr(), cap, C.byref(n)))
+    return out[:n.value]
+
+
+def token_at_tensor(stream, pos: int):
+    """(index of the token holding decoded byte `pos`, decoded position of its first byte)."""
+    import torch
+    assert stream.is_cuda and stream.dtype == torch.uint8 and stream.is_contiguous()
+    init(stream.device.index)
+    torch.cuda.current_stream(stream.device).synchronize()
+    k, p = C.c_long(0), C.c_long(0)
+    _check(load_library().lz77_gpu_token_at_device(stream.data_ptr(), stream.numel(), pos,
+                                                   C.byref(k), C.byref(p)))
+    return k.value, p.value
 
 
 def decode_tensor(stream, out=None):

@@ -636,6 +636,57 @@ int lz77_gpu_decode_size_device(const void *d_in, long n_in, long *n_out)
     return decode_scan_device(d_in, n_in, &P, &k, n_out, nullptr);
 }
 
+int lz77_gpu_slice_tokens_device(const void *d_in, long n_in, long tok_lo, long tok_hi,
+                                 void *d_out, long out_cap, long *n_out)
+{
+    if (!g.ready) return LZ77_E_NODEVICE;
+    if (n_in < 0 || !d_in || !d_out || !n_out) return LZ77_E_ARG;
+    if ((((uintptr_t)d_in) | ((uintptr_t)d_out)) & 15) return LZ77_E_ARG;
+    if (n_in < 4) return LZ77_E_STREAM;
+    CK(cudaSetDevice(g.device));
+    CK(cudaMemcpyAsync(g.pinned, d_in, 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    unsigned char hdr[4];
+    memcpy(hdr, g.pinned, 4);
+    Params P;
+    long long K = 0;
+    int rc = read_header(hdr, n_in, &P, &K);
+    if (rc) return rc;
+    if (tok_lo < 0 || tok_hi < tok_lo || tok_hi > K) return LZ77_E_ARG;
+    const long long bytes = 4 + ((long long)(tok_hi - tok_lo) * P.tbits + 7) / 8;
+    const long long words = (bytes + 3) / 4;
+    if (words * 4 > out_cap) return LZ77_E_SPACE;
+    CK(launch_slice_tokens((const uint32_t *)d_in, n_in, tok_lo, tok_hi, P, (uint32_t *)d_out,
+                           words, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    *n_out = (long)bytes;
+    return LZ77_OK;
+}
+
+int lz77_gpu_token_at_device(const void *d_in, long n_in, long pos, long *tok, long *tok_pos)
+{
+    Params P;
+    long long k = 0;
+    long n = 0;
+    if (!tok || !tok_pos) return LZ77_E_ARG;
+    int rc = decode_scan_device(d_in, n_in, &P, &k, &n, nullptr);
+    if (rc) return rc;
+    if (pos < 0 || pos > n) return LZ77_E_ARG;
+    if (k == 0 || pos == n) {
+        *tok = (long)k;
+        *tok_pos = n;
+        return LZ77_OK;
+    }
+    // the result lands behind the DecodeInfo copy in the pinned staging area
+    long long *d_result = (long long *)((char *)g.scratch + 64);
+    CK(launch_token_at((const uint32_t *)d_in, n_in, k, pos, P, g.scratch, d_result, g.stream));
+    CK(cudaMemcpyAsync(g.pinned, d_result, 16, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    *tok = (long)((const long long *)g.pinned)[0];
+    *tok_pos = (long)((const long long *)g.pinned)[1];
+    return LZ77_OK;
+}
+
 int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_cap, long *n_out)
 {
     Params P;

@@ -189,6 +189,72 @@ __global__ void lz77_decode_publish_kernel(const DecodeInfo *info,
 }
 
 // ---------------------------------------------------------------------------
+// token-array helpers for sharding one stream across GPUs: tokens
+// are fixed width, so a stream splits at any token without parsing
+// ---------------------------------------------------------------------------
+
+// out = the header of `words` + tokens [tok_lo, tok_hi) moved down to bit 32
+__global__ void lz77_slice_tokens_kernel(const uint32_t *__restrict__ words, long long n_words,
+                                         long long bit_lo, long long n_bits,
+                                         uint32_t *__restrict__ out, long long out_words)
+{
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= out_words) return;
+    if (w == 0) {
+        out[0] = words[0];
+        return;
+    }
+    const long long b = (w - 1) * 32;  // first payload bit of this word
+    uint32_t v = b < n_bits ? load_bits32(words, n_words, bit_lo + b) : 0u;
+    if (n_bits - b < 32 && b < n_bits) v &= (1u << (int)(n_bits - b)) - 1u;  // zero padding
+    out[w] = v;
+}
+
+// The token that holds output byte `pos` (or starts there) and its output position:
+// the tile table gives the token covering the tile's first byte, one warp walks on.
+__global__ void lz77_token_at_kernel(const uint32_t *__restrict__ words, long long n_words,
+                                     long long n_tokens, Params P, int tile_shift,
+                                     const long long *__restrict__ tile_tok,
+                                     const long long *__restrict__ tile_pos, long long pos,
+                                     long long *result /* [2] */)
+{
+    const int lane = threadIdx.x;
+    const uint32_t len_mask = (1u << P.lb) - 1u;
+    const long long j = pos >> tile_shift;
+    long long k = tile_tok[j], p = tile_pos[j];
+    while (true) {
+        const long long kk = k + lane;
+        unsigned l1 = 0;
+        if (kk < n_tokens)
+            l1 = ((load_bits32(words, n_words, kHeaderBits + kk * P.tbits) >> P.ob) & len_mask) + 1u;
+        unsigned inc = l1;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, inc, dlt);
+            if (lane >= dlt) inc += t;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, kk < n_tokens && p + (long long)inc > pos);
+        if (m) {
+            const int first = __ffs(m) - 1;
+            if (lane == first) {
+                result[0] = kk;
+                result[1] = p + inc - l1;
+            }
+            return;
+        }
+        p += __shfl_sync(0xffffffffu, inc, 31);
+        k += 32;
+        if (k >= n_tokens) {  // pos == decoded size
+            if (lane == 0) {
+                result[0] = n_tokens;
+                result[1] = p;
+            }
+            return;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // pass 2: tile decode
 // ---------------------------------------------------------------------------
 
@@ -521,6 +587,30 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
 }
 
 long long decode_scan_granule() { return kDsChunk; }
+
+cudaError_t launch_slice_tokens(const uint32_t *d_in_words, long long n_in_bytes,
+                                long long tok_lo, long long tok_hi, const Params &P,
+                                uint32_t *d_out_words, long long out_words, cudaStream_t st)
+{
+    const long long n_words = (n_in_bytes + 3) / 4;
+    const int threads = 256;
+    const long long blocks = (out_words + threads - 1) / threads;
+    lz77_slice_tokens_kernel<<<(unsigned)blocks, threads, 0, st>>>(
+        d_in_words, n_words, kHeaderBits + tok_lo * P.tbits, (tok_hi - tok_lo) * P.tbits,
+        d_out_words, out_words);
+    return cudaGetLastError();
+}
+
+// after launch_decode_scan; result = 2 x int64 in device memory
+cudaError_t launch_token_at(const uint32_t *d_in_words, long long n_in_bytes, long long n_tokens,
+                            long long pos, const Params &P, void *scratch, long long *d_result,
+                            cudaStream_t st)
+{
+    DecodeScratch s = carve_decode(scratch, n_tokens, P);
+    lz77_token_at_kernel<<<1, 32, 0, st>>>(d_in_words, (n_in_bytes + 3) / 4, n_tokens, P,
+                                           P.tile_shift, s.tile_tok, s.tile_pos, pos, d_result);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_decode_scan(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, const Params &P, void *scratch,

@@ -79,6 +79,13 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
                                       long long tile_end, bool last, long long n_out,
                                       int launch_idx, int pair_mode, const Params &P,
                                       void *scratch, uint8_t *d_out, cudaStream_t st);
+// token-array helpers (sharding one stream across GPUs)
+cudaError_t launch_slice_tokens(const uint32_t *d_in_words, long long n_in_bytes,
+                                long long tok_lo, long long tok_hi, const Params &P,
+                                uint32_t *d_out_words, long long out_words, cudaStream_t st);
+cudaError_t launch_token_at(const uint32_t *d_in_words, long long n_in_bytes, long long n_tokens,
+                            long long pos, const Params &P, void *scratch, long long *d_result,
+                            cudaStream_t st);
 // pass 2 (needs the decoded size pass 1 produced): tile decode, or pointer jumping
 // (decode_jump.cu; jump_scratch of decode_jump_scratch_bytes()) when cross_block
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,

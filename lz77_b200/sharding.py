@@ -165,3 +165,115 @@ def encode_sharded(data: torch.Tensor | None, n_bytes: int, sb: int, la: int, bl
     shard = scatter_input(data, n_bytes, block, device, root)
     stream, k = encode_fn(shard, sb, la)
     return gather_stream(stream, k, token_bits, root)
+
+
+# --------------------------------------------------------------------------- #
+# sharded decode of ONE block-structured stream
+# --------------------------------------------------------------------------- #
+
+class DecodeCodec:
+    """The four operations decode_sharded needs, as callables on uint8 tensors of the
+    backend's device (on the GPU box: the ``lz77_b200`` functions of the same names):
+
+      slice_tokens(stream, a, b) -> standalone stream with tokens [a, b)
+      decode_size(stream)        -> decoded size
+      token_at(stream, pos)      -> (token holding decoded byte pos, its decoded position)
+      decode(stream)             -> decoded bytes
+    """
+
+    def __init__(self, slice_tokens, decode_size, token_at, decode):
+        self.slice_tokens, self.decode_size = slice_tokens, decode_size
+        self.token_at, self.decode = token_at, decode
+
+
+def token_slices(n_tokens: int, world: int) -> List[Tuple[int, int]]:
+    """Even split of the token array: [lo, hi) per rank."""
+    return [(n_tokens * r // world, n_tokens * (r + 1) // world) for r in range(world)]
+
+
+def decode_sharded(stream: torch.Tensor | None, block: int, token_bits: int, codec: DecodeCodec,
+                   device, root: int = 0):
+    """Decode one stream of the block-parallel encoder on all ranks.
+
+    Tokens are fixed width, so the token array splits evenly without parsing:
+      1. root sends rank r the tokens [K r/G, K (r+1)/G) plus `block` tokens of margin
+         (a standalone stream each; a token decodes to >= 1 byte, so the margin
+         reaches the next block boundary);
+      2. every rank sums len+1 over its own tokens; one all-gather of the sums gives
+         every slice its decoded position;
+      3. every rank looks up the token that starts the first block at or after its
+         position (a token starts on every block boundary); one all-gather of these
+         split points nudges the slice boundaries to block boundaries;
+      4. every rank decodes its run of whole blocks -- independent by construction --
+         and the outputs travel to root with point-to-point sends.
+    Root returns the decoded bytes (uint8 tensor on `device`), the other ranks None.
+    Streams of the reference encoder are not block-structured (a match may reach
+    back SB bytes from anywhere): replicas only, ValueError here."""
+    dist = _dist()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    meta = torch.zeros(2, dtype=torch.int64, device=device)
+    if rank == root:
+        n_tokens = ((stream.numel() - HEADER_BYTES) * 8) // token_bits
+        meta[0], meta[1] = n_tokens, stream.numel()
+    dist.broadcast(meta, src=root)
+    n_tokens = int(meta[0])
+    if n_tokens // world < block:
+        # fewer than one block of tokens per rank: not worth a split
+        if rank != root:
+            return None
+        return codec.decode(stream)
+
+    slices = token_slices(n_tokens, world)
+    with_margin = [(lo, min(n_tokens, hi + block)) for lo, hi in slices]
+    nbytes = [HEADER_BYTES + ((b - a) * token_bits + 7) // 8 for a, b in with_margin]
+    # 1. token slices (with margin) from root
+    if rank == root:
+        reqs, local = [], None
+        for r, (a, b) in enumerate(with_margin):
+            sub = codec.slice_tokens(stream, a, b)
+            if r == root:
+                local = sub
+            else:
+                reqs.append(dist.isend(sub.contiguous(), dst=r))
+        for q in reqs:
+            q.wait()
+    else:
+        local = torch.empty(nbytes[rank], dtype=torch.uint8, device=device)
+        dist.recv(local, src=root)
+    k_lo, k_hi = slices[rank]
+    # 2. decoded size of the own tokens -> decoded position of every slice
+    own = codec.decode_size(codec.slice_tokens(local, 0, k_hi - k_lo))
+    sums = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sums, torch.tensor([own], dtype=torch.int64, device=device))
+    sums = [int(v) for v in sums.cpu().tolist()]
+    pos = sum(sums[:rank])
+    # 3. first block boundary at or after the slice start -> split token
+    to_boundary = (-pos) % block
+    k_rel, k_pos = codec.token_at(local, to_boundary)
+    if k_pos != to_boundary:
+        raise ValueError("no token starts on the block boundary: not a stream of the block encoder")
+    splits = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(splits, torch.tensor([k_lo + k_rel], dtype=torch.int64,
+                                                     device=device))
+    splits = [int(v) for v in splits.cpu().tolist()] + [n_tokens]
+    a, b = splits[rank] - k_lo, splits[rank + 1] - k_lo
+    # 4. decode the run of whole blocks, gather at root
+    part = codec.decode(codec.slice_tokens(local, a, b)) if b > a else \
+        torch.empty(0, dtype=torch.uint8, device=device)
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(sizes, torch.tensor([part.numel()], dtype=torch.int64,
+                                                    device=device))
+    sizes = [int(v) for v in sizes.cpu().tolist()]
+    if rank != root:
+        if sizes[rank] > 0:
+            dist.send(part.contiguous(), dst=root)
+        return None
+    out = torch.empty(sum(sizes), dtype=torch.uint8, device=device)
+    at = 0
+    for r in range(world):
+        if r == root:
+            out[at:at + sizes[r]] = part
+        elif sizes[r] > 0:
+            dist.recv(out[at:at + sizes[r]], src=r)
+        at += sizes[r]
+    return out

@@ -79,3 +79,35 @@ GOLDEN_CASES = [
     _c("mixed_768k_l32", "mixed", n=768 << 10, seed=23, sb=8191, la=32, segment=128 << 10),
     _c("pow2_sb4096", "zipf_text", n=64 << 10, seed=24, sb=4096, la=16),
 ]
+
+
+# ---- numpy view of a stream's token array (tests only) --------------------------
+
+def stream_params(stream: bytes):
+    import math
+    sb = stream[0] | stream[1] << 8
+    la = stream[2] | stream[3] << 8
+    ob = math.ceil(math.log2(sb)) if sb > 1 else 0
+    lb = math.ceil(math.log2(la))
+    return sb, la, ob, lb, ob + lb + 8
+
+
+def parse_tokens(stream: bytes):
+    """(off, len, lit) arrays of a stream: token k sits at bit 32 + k*T, LSB first
+    (lz77.c:246-252, bitio.c:203-239)."""
+    import numpy as np
+    _, _, ob, lb, T = stream_params(stream)
+    body = np.frombuffer(stream, dtype=np.uint8)[4:]
+    k = (body.size * 8) // T
+    bits = np.unpackbits(body, bitorder="little")[:k * T].reshape(k, T).astype(np.int64)
+    w = (bits << np.arange(T, dtype=np.int64)[None, :]).sum(axis=1)
+    return w & ((1 << ob) - 1), (w >> ob) & ((1 << lb) - 1), w >> (ob + lb)
+
+
+def slice_tokens(stream: bytes, a: int, b: int) -> bytes:
+    """Standalone stream holding tokens [a, b) of `stream`."""
+    import numpy as np
+    T = stream_params(stream)[4]
+    body = np.frombuffer(stream, dtype=np.uint8)[4:]
+    bits = np.unpackbits(body, bitorder="little")[a * T:b * T]
+    return stream[:4] + np.packbits(bits, bitorder="little").tobytes()

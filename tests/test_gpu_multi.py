@@ -1,7 +1,9 @@
 """Multi-GPU sharding over NCCL (skipped on a box with fewer than 2 GPUs): the
 input is scattered as runs of whole blocks, every rank encodes its shard on its
 own GPU, the token payloads are gathered to rank 0 -- the merged stream must be
-byte-identical to the single-GPU stream and decode to the input."""
+byte-identical to the single-GPU stream and decode to the input.  The merged
+stream is then decoded by all ranks together (even token split, slice sums,
+split points nudged to block boundaries) and must give the input again."""
 import os
 import sys
 from pathlib import Path
@@ -38,6 +40,12 @@ def _nccl_worker(rank, world, port, sb, la, n, q):
         single, _ = lz77_b200.encode_tensor(data, la=la, sb=sb)
         ok = merged.tobytes() == single.cpu().numpy().tobytes()
         ok = ok and lz77_b200.decode(merged.tobytes()) == data.cpu().numpy().tobytes()
+    codec = sharding.DecodeCodec(lz77_b200.slice_tokens_tensor, lz77_b200.decode_size_tensor,
+                                 lz77_b200.token_at_tensor, lz77_b200.decode_tensor)
+    stream = torch.from_numpy(merged.copy()).to(dev) if rank == 0 else None
+    out = sharding.decode_sharded(stream, block, T, codec, dev)
+    if rank == 0:
+        ok = ok and torch.equal(out, data)
         q.put(ok)
     dist.barrier()
     dist.destroy_process_group()
@@ -53,7 +61,7 @@ def test_sharded_encode_nccl(sb, la):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 1000) + sb % 7
-    n = 37 * 65536 + 4321
+    n = 37 * 65536 + 4321 if sb != 65535 else 24 * 524288 + 4321  # >= 1 block of tokens per rank
     procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, sb, la, n, q))
              for r in range(world)]
     for p in procs:

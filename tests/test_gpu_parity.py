@@ -509,3 +509,35 @@ def test_decode_unblocked_after_blocked_prefix_pipelined(lz, orc):
     import torch
     s = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
     assert api.decode_tensor(s).cpu().numpy().tobytes() == want
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (1000, 20), (65535, 255), (15, 8)])
+def test_token_array_helpers(lz, orc, sb, la):
+    """lz77_gpu_slice_tokens_device / lz77_gpu_token_at_device against a numpy view of the
+    token array (the pieces multi-GPU decode is made of)."""
+    import torch
+    from _cases import parse_tokens, slice_tokens
+    from lz77_b200 import synth
+    data = synth.zipf_text(1_500_000, seed=31).numpy().tobytes()
+    stream = lz.encode(data, la=la, sb=sb)
+    _, length, _ = parse_tokens(stream)
+    start = np.concatenate([[0], np.cumsum(length + 1)])
+    k = len(length)
+    s = torch.frombuffer(bytearray(stream), dtype=torch.uint8).cuda()
+    rng = np.random.default_rng(sb)
+    for a, b in [(0, k), (0, 0), (k, k), (1, 2), (k // 3, 2 * k // 3), (k - 1, k)] + \
+            [tuple(sorted(rng.integers(0, k + 1, size=2))) for _ in range(6)]:
+        sub = lz.slice_tokens_tensor(s, int(a), int(b))
+        assert sub.cpu().numpy().tobytes() == slice_tokens(stream, int(a), int(b)), (a, b)
+        assert lz.decode_size_tensor(sub) == int(start[b] - start[a])
+    for pos in [0, 1, len(data) - 1, len(data), lz.block_size(sb), 3 * lz.block_size(sb) + 17] + \
+            [int(v) for v in rng.integers(0, len(data), size=12)]:
+        if pos > len(data):
+            continue
+        want = int(np.searchsorted(start, pos, side="right") - 1)
+        got = lz.token_at_tensor(s, pos)
+        assert got == (want, int(start[want])), pos
+    with pytest.raises(lz.Lz77Error):
+        lz.token_at_tensor(s, len(data) + 1)
+    with pytest.raises(lz.Lz77Error):
+        lz.slice_tokens_tensor(s, 0, k + 1)

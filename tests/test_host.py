@@ -190,6 +190,74 @@ def _gloo_worker(rank, world, port, sb, la, n, q):
     dist.destroy_process_group()
 
 
+def _gloo_decode_worker(rank, world, port, sb, la, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch
+    import torch.distributed as dist
+    from _cases import parse_tokens, slice_tokens
+    from lz77_b200 import api, sharding, synth
+    from oracle import oracle
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    orc = oracle()
+    lib = api.load_library()
+    block, seg = lib.lz77_gpu_block_size(sb), lib.lz77_gpu_segment_size()
+    T = lib.lz77_token_bits(sb, la)
+
+    def t2b(t):
+        return t.numpy().tobytes()
+
+    def b2t(b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8)
+
+    def token_at(s, pos):  # numpy stand-in for lz77_gpu_token_at_device
+        _, length, _ = parse_tokens(t2b(s))
+        start = np.concatenate([[0], np.cumsum(length + 1)])
+        k = int(np.searchsorted(start, pos, side="right") - 1)
+        return k, int(start[k])
+
+    codec = sharding.DecodeCodec(
+        slice_tokens=lambda s, a, b: b2t(slice_tokens(t2b(s), a, b)),
+        decode_size=lambda s: int((parse_tokens(t2b(s))[1] + 1).sum()),
+        token_at=token_at,
+        decode=lambda s: b2t(orc.decode(t2b(s))))
+    data = synth.zipf_text(n, seed=8).numpy()
+    stream = None
+    if rank == 0:
+        whole, _ = orc.blocked_encode(data, sb, la, block, seg)
+        stream = b2t(whole)
+    out = sharding.decode_sharded(stream, block, T, codec, "cpu")
+    if rank == 0:
+        k = ((stream.numel() - 4) * 8) // T
+        q.put((t2b(out) == data.tobytes(), k // world >= block))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sb,la,n,split", [(4095, 15, 24 * 65536 + 999, True),
+                                           (1000, 20, 16 * 65536 + 5, True),
+                                           (4095, 15, 70_000, False)])
+def test_sharded_decode_world2_gloo(sb, la, n, split):
+    """One block-structured stream decoded by a 2-rank gloo group: even token split,
+    all-gather of the slice sums, split points nudged to block boundaries (the last
+    case is too small to split and decodes on root alone)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + (n % 13)
+    procs = [ctx.Process(target=_gloo_decode_worker, args=(r, 2, port, sb, la, n, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, was_split = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and was_split == split
+
+
 @pytest.mark.parametrize("sb,la", [(4095, 15), (1000, 20)])
 def test_sharded_encode_world2_gloo(sb, la):
     """scatter -> per-rank encode -> gather over a 2-rank gloo group gives the
