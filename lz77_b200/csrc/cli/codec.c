@@ -68,36 +68,6 @@ static void bind_device(void)
         die("initialising the GPU", rc);
 }
 
-/* read the rest of a stream into pinned memory; returns NULL on a read error */
-static unsigned char *slurp(FILE *f, long *n_out)
-{
-    long cap = 1L << 24, n = 0;
-    unsigned char *buf = lz77_gpu_host_alloc(cap);
-    if (buf == NULL)
-        die("allocating the input buffer", LZ77_E_NOMEM);
-    for (;;) {
-        size_t got = fread(buf + n, 1, (size_t)(cap - n), f);
-        n += (long)got;
-        if (n < cap)
-            break;
-        {
-            unsigned char *bigger = lz77_gpu_host_alloc(cap * 2);
-            if (bigger == NULL)
-                die("allocating the input buffer", LZ77_E_NOMEM);
-            memcpy(bigger, buf, (size_t)n);
-            lz77_gpu_host_free(buf);
-            buf = bigger;
-            cap *= 2;
-        }
-    }
-    if (ferror(f)) {
-        lz77_gpu_host_free(buf);
-        return NULL;
-    }
-    *n_out = n;
-    return buf;
-}
-
 /* Bytes of input encoded per library call.  The encoder's blocks are independent,
  * so the stream of a large file is the streams of its pieces back to back: the
  * file never has to fit in (pinned) memory, like the reference's O(1)-memory
@@ -201,35 +171,158 @@ void encode(FILE *file, struct bitFILE *out, int la, int sb)
         lz77_gpu_host_free(obuf);
 }
 
+/* copies nbits bits from bit src_bit of src to bit dst_bit of dst (LSB-first bit
+ * numbering, bitio.c:203-298); the bits of dst behind the copy must be zero */
+static void copy_bits(unsigned char *dst, long dst_bit, const unsigned char *src, long src_bit,
+                      long nbits)
+{
+    if (((dst_bit | src_bit) & 7) == 0) {
+        memcpy(dst + (dst_bit >> 3), src + (src_bit >> 3), (size_t)(nbits >> 3));
+        dst_bit += nbits & ~7L;
+        src_bit += nbits & ~7L;
+        nbits &= 7;
+    }
+    while (nbits > 0) {
+        /* up to 8 bits that end at a source byte boundary */
+        int s_off = (int)(src_bit & 7), d_off = (int)(dst_bit & 7);
+        int take = 8 - s_off;
+        unsigned v;
+        if (take > nbits)
+            take = (int)nbits;
+        v = ((unsigned)src[src_bit >> 3] >> s_off) & ((1u << take) - 1u);
+        dst[dst_bit >> 3] |= (unsigned char)(v << d_off);
+        if (d_off + take > 8)
+            dst[(dst_bit >> 3) + 1] |= (unsigned char)(v >> (8 - d_off));
+        src_bit += take;
+        dst_bit += take;
+        nbits -= take;
+    }
+}
+
+static long env_mib(const char *name, long dflt)
+{
+    const char *e = getenv(name);
+    long mib = e ? atol(e) : dflt;
+    return (mib < 1 ? 1 : mib) << 20;
+}
+
+/*
+ * The stream is decoded in pieces of tokens, so neither the compressed file nor
+ * the output has to fit in memory (the reference's loop keeps SB bytes,
+ * lz77.c:160-195).  Tokens are fixed width, so a piece is any run of whole tokens;
+ * what a piece needs from its past is at most the last SB output bytes (lz77.c:184).
+ * Every library call therefore gets a standalone stream: the header, the retained
+ * output tail re-encoded as literal tokens (off 0, len 0, next = byte), then the
+ * piece's tokens; the tail's bytes are dropped from the result.  The tail starts on a
+ * block boundary of the output, so a stream of the block encoder stays aligned to
+ * its blocks (and keeps decoding block-parallel).
+ */
 void decode(struct bitFILE *file, FILE *out)
 {
-    long n_in = 0, n_out = 0, n = 0;
-    unsigned char *in, *obuf;
-    int rc;
+    unsigned char hdr[4];
+    unsigned char *raw, *sbuf = NULL, *obuf = NULL, *hist;
+    long sbuf_cap = 0, obuf_cap = 0, hist_len = 0, raw_cap, piece_tokens;
+    long out_limit = env_mib("LZ77_CLI_OUT_MIB", 4096);
+    int sb, la, ob, lb, tbits, rc, last = 0;
+    long block;
 
     bind_device();
-    in = slurp(file->file, &n_in);
-    if (in == NULL) {
-        perror("Error reading bits"); /* lz77.c:273-277 */
-        exit(EXIT_FAILURE);
-    }
-    if (n_in < 4) {
+    if (fread(hdr, 1, 4, file->file) != 4) {
         /* the reference reads garbage parameters from a short header and
          * produces an empty file; keep the empty output, flag nothing */
-        lz77_gpu_host_free(in);
         return;
     }
-    rc = lz77_gpu_decode_size(in, n_in, &n_out);
-    if (rc != LZ77_OK)
-        die("decoding", rc);
-    obuf = lz77_gpu_host_alloc(n_out + 16);
-    if (obuf == NULL)
-        die("allocating the output buffer", LZ77_E_NOMEM);
-    rc = lz77_gpu_decode(in, n_in, obuf, n_out, &n);
-    if (rc != LZ77_OK)
-        die("decoding", rc);
-    if (fwrite(obuf, 1, (size_t)n, out) != (size_t)n)
-        perror("Writing output file");
-    lz77_gpu_host_free(in);
-    lz77_gpu_host_free(obuf);
+    sb = hdr[0] | (hdr[1] << 8);
+    la = hdr[2] | (hdr[3] << 8);
+    if (sb < 1 || la < 1 || la > LZ77_MAX_LA)
+        die("decoding", LZ77_E_STREAM);
+    ob = lz77_bitof(sb);
+    lb = lz77_bitof(la);
+    tbits = ob + lb + 8;
+    block = lz77_gpu_block_size(sb);
+    /* whole tokens, a whole number of bytes */
+    piece_tokens = ((piece_bytes() / 4) * 8 / tbits) & ~7L;
+    if (piece_tokens < 8)
+        piece_tokens = 8;
+    raw_cap = piece_tokens / 8 * tbits;
+    raw = malloc((size_t)raw_cap + 8);
+    hist = malloc((size_t)(2 * block));
+    if (raw == NULL || hist == NULL)
+        die("allocating the input buffer", LZ77_E_NOMEM);
+
+    while (!last) {
+        long got = (long)fread(raw, 1, (size_t)raw_cap, file->file);
+        long n_tok, cursor = 0;
+        if (ferror(file->file)) {
+            perror("Error reading bits"); /* lz77.c:273-277 */
+            exit(EXIT_FAILURE);
+        }
+        last = got < raw_cap;
+        /* lz77.c:271-280: a short read ends the stream, trailing bits < T are padding */
+        n_tok = last ? (got * 8) / tbits : piece_tokens;
+        while (cursor < n_tok) {
+            long take = n_tok - cursor, n = 0, m = 0, need, bit, i;
+            for (;;) {
+                need = 4 + ((hist_len + take) * tbits + 7) / 8 + 16;
+                if (need > sbuf_cap) {
+                    if (sbuf != NULL)
+                        lz77_gpu_host_free(sbuf);
+                    sbuf_cap = need + need / 4;
+                    sbuf = lz77_gpu_host_alloc(sbuf_cap);
+                    if (sbuf == NULL)
+                        die("allocating the input buffer", LZ77_E_NOMEM);
+                }
+                memset(sbuf, 0, (size_t)need);
+                memcpy(sbuf, hdr, 4);
+                bit = 32;
+                for (i = 0; i < hist_len; i++) { /* the tail as literal tokens */
+                    unsigned char v[5];
+                    unsigned long long t = (unsigned long long)hist[i] << (ob + lb);
+                    v[0] = (unsigned char)t, v[1] = (unsigned char)(t >> 8);
+                    v[2] = (unsigned char)(t >> 16), v[3] = (unsigned char)(t >> 24);
+                    v[4] = (unsigned char)(t >> 32);
+                    copy_bits(sbuf, bit, v, 0, tbits);
+                    bit += tbits;
+                }
+                copy_bits(sbuf, bit, raw, cursor * tbits, take * tbits);
+                bit += take * tbits;
+                rc = lz77_gpu_decode_size(sbuf, (bit + 7) / 8, &n);
+                if (rc != LZ77_OK)
+                    die("decoding", rc);
+                if (n - hist_len <= out_limit || take <= 8)
+                    break;
+                take = (take / 2 + 7) & ~7L; /* highly compressible: smaller piece */
+            }
+            if (n + 16 > obuf_cap) {
+                if (obuf != NULL)
+                    lz77_gpu_host_free(obuf);
+                obuf_cap = n + n / 4 + 16;
+                obuf = lz77_gpu_host_alloc(obuf_cap);
+                if (obuf == NULL)
+                    die("allocating the output buffer", LZ77_E_NOMEM);
+            }
+            rc = lz77_gpu_decode(sbuf, (bit + 7) / 8, obuf, obuf_cap, &m);
+            if (rc != LZ77_OK)
+                die("decoding", rc);
+            if (m > hist_len &&
+                fwrite(obuf + hist_len, 1, (size_t)(m - hist_len), out) != (size_t)(m - hist_len))
+                perror("Writing output file");
+            /* obuf starts on a block boundary of the output (or at its start): keep from
+             * the last-but-one block boundary on, at least `block` > SB bytes */
+            {
+                long keep = (m % block) + block;
+                if (keep > m)
+                    keep = m;
+                memcpy(hist, obuf + (m - keep), (size_t)keep);
+                hist_len = keep;
+            }
+            cursor += take;
+        }
+    }
+    free(raw);
+    free(hist);
+    if (sbuf != NULL)
+        lz77_gpu_host_free(sbuf);
+    if (obuf != NULL)
+        lz77_gpu_host_free(obuf);
 }

@@ -361,6 +361,38 @@ def test_cli_streams_large_files_in_pieces(lz, orc, tmp_path, args):
     assert len(one.read_bytes()) == 4
 
 
+@pytest.mark.parametrize("args", [[], ["-s", "1000", "-l", "20"], ["-s", "65535", "-l", "255"]])
+def test_cli_decodes_large_files_in_pieces(lz, orc, tmp_path, args):
+    """The command-line decoder works through the stream in pieces of whole tokens
+    (256 MiB of stream by default, 256 KiB here; at most 1 MiB of output per call
+    here), carrying the output tail from piece to piece: block streams and
+    reference-style (unblocked) streams, byte-aligned and 23-bit tokens."""
+    from lz77_b200 import synth
+    cli = ROOT / "lz77_b200" / "bin" / "lz77"
+    text = synth.zipf_text(4 * (1 << 20) + 777, seed=56).numpy().tobytes()
+    data = text[:3_000_000] + bytes(3 << 20) + text[3_000_000:]  # a long run: tiny tokens, big output
+    fin, own, back = tmp_path / "in.bin", tmp_path / "own.lz", tmp_path / "back.bin"
+    fin.write_bytes(data)
+    subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(own), *args], check=True)
+    env = dict(os.environ, LZ77_CLI_PIECE_MIB="1", LZ77_CLI_OUT_MIB="1")
+    subprocess.run([str(cli), "-d", "-i", str(own), "-o", str(back)], check=True, env=env)
+    assert back.read_bytes() == data
+    # a stream of the reference encoder (restated): matches cross every piece seam
+    sb = int(args[1]) if args else 4095
+    la = int(args[3]) if args else 15
+    small = text[:1_200_000] + bytes(70_000) + text[1_200_000:1_500_000]
+    ref = tmp_path / "ref.lz"
+    ref.write_bytes(orc.ref_encode(small, sb, la))
+    env = dict(os.environ, LZ77_CLI_PIECE_MIB="1", LZ77_CLI_OUT_MIB="1")
+    subprocess.run([str(cli), "-d", "-i", str(ref), "-o", str(back)], check=True, env=env)
+    assert back.read_bytes() == small
+    # header only / short header
+    for blob in (ref.read_bytes()[:4], b"\xff\x0f"):
+        ref.write_bytes(blob)
+        subprocess.run([str(cli), "-d", "-i", str(ref), "-o", str(back)], check=True, env=env)
+        assert back.read_bytes() == b""
+
+
 def test_device_buffers_must_be_aligned(lz):
     """The device entry points move 128-bit words / TMA bulk copies: a misaligned
     pointer is refused, not dereferenced."""
