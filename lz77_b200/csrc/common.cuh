@@ -25,7 +25,7 @@ struct Params {
     long long block;   // independent block size in bytes (power of two)
     int block_shift;
     int tile_shift;    // decode tile = min(block, 128 KiB): what fits shared memory (a
-                       // 256 KiB block is decoded as two tiles)
+                       // 512 KiB block is decoded as four tiles)
 };
 
 __host__ __device__ inline int bitof(int n)  // bitio.c:41-43 in integers

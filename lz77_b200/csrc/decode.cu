@@ -514,7 +514,7 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
 
 int decode_tile_bytes(const Params &P)
 {
-    return 1 << P.tile_shift;  // the encoder block, or half of a 256 KiB block
+    return 1 << P.tile_shift;  // the encoder block, or a quarter of a 512 KiB block
 }
 
 static inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }

@@ -417,10 +417,10 @@ def test_device_buffers_must_be_aligned(lz):
                                             ("random", 4095, 15, 0.02), ("zipf_text", 65535, 255, 0.03),
                                             ("random", 65535, 255, 0.02)])
 def test_compressed_size_close_to_reference(lz, orc, kind, sb, la, tol):
-    """Block cuts (64 / 256 KiB) and parse restarts (1 KiB) are the only reasons the
+    """Block cuts (64 / 512 KiB) and parse restarts (1 KiB) are the only reasons the
     stream is longer than the reference's: within 2 % at the default parameters,
-    5 % at the 64 KiB window, where every 256 KiB block starts with an empty window
-    (measured 4.2 % on text, 2.9 % on random data; DESIGN.md sections 2 and 9)."""
+    3 % at the 64 KiB window, where every 512 KiB block starts with an empty window
+    (measured 2.2 % on text, 1.4 % on random data; DESIGN.md sections 2 and 9)."""
     from lz77_b200 import synth
     data = synth.make(kind, 3 << 20, seed=61).numpy().tobytes()
     ours = len(lz.encode(data, la=la, sb=sb))
