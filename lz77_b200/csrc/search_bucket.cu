@@ -140,6 +140,39 @@ __device__ __forceinline__ int match_len_s(uint32_t sdata, int q, int p0,
     }
 }
 
+// One candidate per lane of a round, LA <= 16.  The first four bytes are compared
+// without a branch by every lane -- a lane without a candidate (`in` false) reads the
+// target itself and is masked afterwards -- because most candidates end there and a
+// divergent round costs every path once; only lanes whose first word matches go on.
+__device__ __forceinline__ int round_match_len(uint32_t sdata, int q, bool in, int p0,
+                                               const uint32_t (&tgt)[4], int max_len)
+{
+    const int qq = in ? q : p0;
+    const uint32_t w = sdata + (uint32_t)(qq & ~3);
+    const int sh = (qq & 3) * 8;
+    const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
+    uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+    int l = (int)min((uint32_t)(__ffs(x) - 1) >> 3, 4u);  // __ffs(0) - 1 wraps: 4
+    if (in && x == 0u) {
+        const uint32_t a2 = lds32(w + 8);
+        x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+        if (x) {
+            l = 4 + ((__ffs(x) - 1) >> 3);
+        } else {
+            const uint32_t a3 = lds32(w + 12);
+            x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+            if (x) {
+                l = 8 + ((__ffs(x) - 1) >> 3);
+            } else {
+                const uint32_t a4 = lds32(w + 16);
+                x = __funnelshift_r(a3, a4, sh) ^ tgt[3];
+                l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
+            }
+        }
+    }
+    return in ? min(l, max_len) : 0;
+}
+
 // first index in [0, n) of the ascending uint16 list at shared address se whose
 // value is >= lo (n if none); uniform across the kLanes lanes of a group
 template <int kLanes>
@@ -169,6 +202,9 @@ __device__ __forceinline__ int group_lower_bound_s(uint32_t se, int n, int lo, i
 // parses 32 / kLanes segments side by side: the per-token scalar work (target
 // load, bucket lookup, window bound, reduction, emit) is issued once for all
 // the groups of a warp that are in step.
+#ifndef LZ77_EMIT_ROWS
+#define LZ77_EMIT_ROWS 0
+#endif
 #ifndef LZ77_PARSE_MINBLOCKS
 #define LZ77_PARSE_MINBLOCKS 1
 #endif
@@ -279,16 +315,18 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
         for (int r = 0; r < rows; r++) {
             const int i = cbase + r * 32 + lane;
             const bool valid = i < cend;
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            // every lane takes part (a lane past the end with a key of its own): a
+            // shuffle under a partial mask costs a second MATCH.ANY, the slowest
+            // instruction of the build
+            const int key = valid ? bucket_key(smem, i) : kBuckets + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader)
+                old = atomicAdd(&cnt[key * (kWarps / 2) + cnt_col],
+                                (uint32_t)__popc(peers) << cnt_sh);
+            old = __shfl_sync(0xffffffffu, old, leader);
             if (valid) {
-                const int key = bucket_key(smem, i);
-                const unsigned peers = __match_any_sync(vmask, key);
-                const int leader = __ffs(peers) - 1;
-                uint32_t old = 0;
-                if (lane == leader)
-                    old = atomicAdd(&cnt[key * (kWarps / 2) + cnt_col],
-                                    (uint32_t)__popc(peers) << cnt_sh);
-                old = __shfl_sync(peers, old, leader);
                 const int slot = (int)bstart[key] + (int)((old >> cnt_sh) & 0xffffu) +
                                  __popc(peers & lt_mask);
                 sorted[slot] = (PosT)i;
@@ -307,11 +345,13 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             const int seg_end = (int)(seg_hi - src_lo) + dst0;
             int p0 = (int)(seg_lo - src_lo) + dst0;
             const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // may be < 0
-            uint32_t *tok_row = tok_tmp + sgm * kSegBytes + sl;  // this lane's slot in the row
+            uint32_t *tok_row = tok_tmp + sgm * kSegBytes;
             const int len_shift = P.ob, lit_shift = P.ob + P.lb;
             const int la = P.la, window = P.window;
             int ntok = 0;
+#if LZ77_EMIT_ROWS
             uint32_t held = 0;
+#endif
 
             while (p0 < seg_end) {
                 const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
@@ -346,9 +386,16 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     for (; i < bn; i += kLanes) {
                         const int idx = i + sl;
                         const int q = idx < bn ? (int)lds16(se + 2u * idx) : 0x7fffffff;
-                        if (q >= lo_idx && q < p0) {
+                        const bool in = q >= lo_idx && q < p0;
+                        if (kSmallLA) {
+                            const int l = round_match_len(sdata, q, in, p0, tgt, max_len);
                             // nearer than anything this lane has seen: must be longer
-                            const int l = match_len_s<kSmallLA>(sdata, q, p0, tgt, max_len);
+                            if (l > best_len) {
+                                best_len = l;
+                                best_q = q;
+                            }
+                        } else if (in) {
+                            const int l = match_len_s<false>(sdata, q, p0, tgt, max_len);
                             if (l > best_len) {
                                 best_len = l;
                                 best_q = q;
@@ -398,15 +445,23 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                 const uint32_t lit = lds8(sdata + (uint32_t)(p0 + len));
                 const uint32_t tok =
                     (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
+#if LZ77_EMIT_ROWS
                 if (sl == (ntok & (kLanes - 1))) held = tok;
                 ntok++;
                 if ((ntok & (kLanes - 1)) == 0) {  // a full row: one coalesced store
-                    *tok_row = held;
-                    tok_row += kLanes;
+                    tok_row[ntok - kLanes + sl] = held;
                 }
                 p0 += len + 1;
             }
-            if (sl < (ntok & (kLanes - 1))) *tok_row = held;
+            if (sl < (ntok & (kLanes - 1))) tok_row[(ntok & ~(kLanes - 1)) + sl] = held;
+#else
+                // one 4-byte store per token by one lane: fewer instructions than
+                // collecting rows of 32 tokens in registers, and L2 merges the sectors
+                if (sl == 0) tok_row[ntok] = tok;
+                ntok++;
+                p0 += len + 1;
+            }
+#endif
             if (sl == 0) seg_ntok[sgm] = (uint32_t)ntok;
         }
         __syncthreads();  // the next tile overwrites the staged data and the buckets
