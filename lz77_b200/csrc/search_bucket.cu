@@ -30,6 +30,18 @@ namespace lz77 {
 // Bucket key: the low kKeyBits bits of each of the two bytes.  For lowercase text
 // this is a perfect hash of the byte pair (one bucket per digram); for binary
 // data it spreads the 65536 pairs evenly.
+// tuning knobs, measured on 256 MiB of text (B200): rows of the scatter issued in
+// batches of 1 / 2 / 4 / 8 -> 9.01 / 9.28 / 9.52 / 9.79 ms (MATCH.ANY back to back stalls
+// the pipe); reading bytes 8..15 of the target on demand -> 9.15 -> 9.01 ms
+#ifndef LZ77_SCATTER_BATCH
+#define LZ77_SCATTER_BATCH 1
+#endif
+#ifndef LZ77_BALLOT_RANK
+#define LZ77_BALLOT_RANK 0
+#endif
+#ifndef LZ77_LAZY_TGT
+#define LZ77_LAZY_TGT 1
+#endif
 #ifndef LZ77_KEY_BITS
 #define LZ77_KEY_BITS 5
 #endif
@@ -145,27 +157,32 @@ __device__ __forceinline__ int match_len_s(uint32_t sdata, int q, int p0,
 // target itself and is masked afterwards -- because most candidates end there and a
 // divergent round costs every path once; only lanes whose first word matches go on.
 __device__ __forceinline__ int round_match_len(uint32_t sdata, int q, bool in, int p0,
-                                               const uint32_t (&tgt)[4], int max_len)
+                                               uint32_t tgt0, uint32_t tgt1, uint32_t tgt2,
+                                               uint32_t tgt3, int max_len)
 {
     const int qq = in ? q : p0;
     const uint32_t w = sdata + (uint32_t)(qq & ~3);
     const int sh = (qq & 3) * 8;
     const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
-    uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+    uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt0;
     int l = (int)min((uint32_t)(__ffs(x) - 1) >> 3, 4u);  // __ffs(0) - 1 wraps: 4
     if (in && x == 0u) {
         const uint32_t a2 = lds32(w + 8);
-        x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+        x = __funnelshift_r(a1, a2, sh) ^ tgt1;
         if (x) {
             l = 4 + ((__ffs(x) - 1) >> 3);
         } else {
+            // bytes 8..15 of the target are rarely needed: read them here, not per token
+            const uint32_t pw = sdata + (uint32_t)(p0 & ~3);
+            const int psh = (p0 & 3) * 8;
+            const uint32_t t2 = lds32(pw + 8), t3 = lds32(pw + 12), t4 = lds32(pw + 16);
             const uint32_t a3 = lds32(w + 12);
-            x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+            x = __funnelshift_r(a2, a3, sh) ^ (LZ77_LAZY_TGT ? __funnelshift_r(t2, t3, psh) : tgt2);
             if (x) {
                 l = 8 + ((__ffs(x) - 1) >> 3);
             } else {
                 const uint32_t a4 = lds32(w + 16);
-                x = __funnelshift_r(a3, a4, sh) ^ tgt[3];
+                x = __funnelshift_r(a3, a4, sh) ^ (LZ77_LAZY_TGT ? __funnelshift_r(t3, t4, psh) : tgt3);
                 l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
             }
         }
@@ -312,24 +329,49 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             if (threadIdx.x == kThreads - 1) bstart[kBuckets] = (PosT)base;
         }
         __syncthreads();
-        for (int r = 0; r < rows; r++) {
-            const int i = cbase + r * 32 + lane;
-            const bool valid = i < cend;
-            // every lane takes part (a lane past the end with a key of its own): a
-            // shuffle under a partial mask costs a second MATCH.ANY, the slowest
-            // instruction of the build
-            const int key = valid ? bucket_key(smem, i) : kBuckets + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (valid && lane == leader)
-                old = atomicAdd(&cnt[key * (kWarps / 2) + cnt_col],
-                                (uint32_t)__popc(peers) << cnt_sh);
-            old = __shfl_sync(0xffffffffu, old, leader);
-            if (valid) {
-                const int slot = (int)bstart[key] + (int)((old >> cnt_sh) & 0xffffu) +
-                                 __popc(peers & lt_mask);
-                sorted[slot] = (PosT)i;
+        // Every lane takes part -- a lane past the end with a key of its own -- because a
+        // shuffle under a partial mask costs a second MATCH.ANY, the slowest instruction
+        // of the build.  (kBatch rows can be issued together; one at a time is fastest.)
+        constexpr int kBatch = LZ77_SCATTER_BATCH;
+        for (int r0 = 0; r0 < rows; r0 += kBatch) {
+            int key[kBatch];
+            unsigned peers[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; b++) {
+                const int i = cbase + (r0 + b) * 32 + lane;
+                key[b] = (r0 + b < rows && i < cend) ? bucket_key(smem, i) : kBuckets + lane;
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; b++) {
+#if LZ77_BALLOT_RANK
+                unsigned m = 0xffffffffu;
+#pragma unroll
+                for (int bit = 0; bit < 2 * kKeyBits + 1; bit++) {
+                    const bool one = (key[b] >> bit) & 1;
+                    const unsigned bal = __ballot_sync(0xffffffffu, one);
+                    m &= one ? bal : ~bal;
+                }
+                // (lanes past the end carry bit 2*kKeyBits and differ among themselves)
+                peers[b] = key[b] < kBuckets ? m : 1u << lane;
+#else
+                peers[b] = __match_any_sync(0xffffffffu, key[b]);
+#endif
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; b++) {
+                const int i = cbase + (r0 + b) * 32 + lane;
+                const bool valid = key[b] < kBuckets;
+                const int leader = __ffs(peers[b]) - 1;
+                uint32_t old = 0;
+                if (valid && lane == leader)
+                    old = atomicAdd(&cnt[key[b] * (kWarps / 2) + cnt_col],
+                                    (uint32_t)__popc(peers[b]) << cnt_sh);
+                old = __shfl_sync(0xffffffffu, old, leader);
+                if (valid) {
+                    const int slot = (int)bstart[key[b]] + (int)((old >> cnt_sh) & 0xffffu) +
+                                     __popc(peers[b] & lt_mask);
+                    sorted[slot] = (PosT)i;
+                }
             }
         }
         if (kSortedGlobal) __threadfence_block();
@@ -365,12 +407,16 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                     {
                         const uint32_t w = sdata + (uint32_t)(p0 & ~3);
                         const int sh = (p0 & 3) * 8;
-                        const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
-                        const uint32_t a2 = lds32(w + 8), a3 = lds32(w + 12), a4 = lds32(w + 16);
+                        const uint32_t a0 = lds32(w), a1 = lds32(w + 4), a2 = lds32(w + 8);
                         tgt[0] = __funnelshift_r(a0, a1, sh);
                         tgt[1] = __funnelshift_r(a1, a2, sh);
-                        tgt[2] = __funnelshift_r(a2, a3, sh);
-                        tgt[3] = __funnelshift_r(a3, a4, sh);
+                        if (!kSmallLA || !LZ77_LAZY_TGT) {  // (LA <= 16 reads bytes 8..15 on demand)
+                            const uint32_t a3 = lds32(w + 12), a4 = lds32(w + 16);
+                            tgt[2] = __funnelshift_r(a2, a3, sh);
+                            tgt[3] = __funnelshift_r(a3, a4, sh);
+                        } else {
+                            tgt[2] = tgt[3] = 0u;
+                        }
                     }
                     const int key = pair_key(tgt[0], tgt[0] >> 8);
                     const int bs = (int)lds16(sbstart + 2u * key);
@@ -388,7 +434,8 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                         const int q = idx < bn ? (int)lds16(se + 2u * idx) : 0x7fffffff;
                         const bool in = q >= lo_idx && q < p0;
                         if (kSmallLA) {
-                            const int l = round_match_len(sdata, q, in, p0, tgt, max_len);
+                            const int l = round_match_len(sdata, q, in, p0, tgt[0], tgt[1], tgt[2], tgt[3],
+                                                          max_len);
                             // nearer than anything this lane has seen: must be longer
                             if (l > best_len) {
                                 best_len = l;
@@ -403,9 +450,9 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                         }
                         if (__any_sync(gmask, best_len >= max_len || q >= p0)) break;
                     }
+                    // (no candidate: length 0 in the top bits, the start is not used)
                     const uint32_t k = __reduce_max_sync(
-                        gmask, best_len ? ((uint32_t)best_len << 20) |
-                                              (0xfffffu - (uint32_t)best_q) : 0u);
+                        gmask, ((uint32_t)best_len << 20) | (0xfffffu - (uint32_t)best_q));
                     len = (int)(k >> 20);
                     int q_best = (int)(0xfffffu - (k & 0xfffffu));
                     if (len < 2) {
