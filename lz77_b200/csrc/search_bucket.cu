@@ -390,9 +390,11 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             uint32_t *tok_row = tok_tmp + sgm * kSegBytes;
             const int len_shift = P.ob, lit_shift = P.ob + P.lb;
             const int la = P.la, window = P.window;
-            int ntok = 0;
 #if LZ77_EMIT_ROWS
+            int ntok = 0;
             uint32_t held = 0;
+#else
+            uint32_t *tok_at = tok_row;  // a running pointer: no address arithmetic per token
 #endif
 
             while (p0 < seg_end) {
@@ -504,10 +506,11 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
 #else
                 // one 4-byte store per token by one lane: fewer instructions than
                 // collecting rows of 32 tokens in registers, and L2 merges the sectors
-                if (sl == 0) tok_row[ntok] = tok;
-                ntok++;
+                if (sl == 0) *tok_at = tok;
+                tok_at++;
                 p0 += len + 1;
             }
+            const int ntok = (int)(tok_at - tok_row);
 #endif
             if (sl == 0) seg_ntok[sgm] = (uint32_t)ntok;
         }
