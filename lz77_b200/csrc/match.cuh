@@ -70,4 +70,37 @@ __device__ __forceinline__ int match_len(const uint8_t *smem, int q, int p0,
     }
 }
 
+// The same from byte 4 on, for a caller that has already found bytes 0..3 equal
+// (w, sh as above, a1 = w[1]).
+template <bool kSmallLA>
+__device__ __forceinline__ int match_len_from4(const uint8_t *smem, const uint32_t *w, int sh,
+                                               uint32_t a1, int p0, const uint32_t (&tgt)[4],
+                                               int max_len)
+{
+    uint32_t a2 = w[2];
+    uint32_t x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+    if (x) return min(4 + ((__ffs(x) - 1) >> 3), max_len);
+    uint32_t a3 = w[3];
+    x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+    if (x) return min(8 + ((__ffs(x) - 1) >> 3), max_len);
+    uint32_t a = w[4];
+    x = __funnelshift_r(a3, a, sh) ^ tgt[3];
+    if (x) return min(12 + ((__ffs(x) - 1) >> 3), max_len);
+    int l = 16;
+    if (!kSmallLA) {
+        int wi = 5;
+        while (l < max_len) {
+            uint32_t b = w[wi++];
+            x = __funnelshift_r(a, b, sh) ^ lds_u32_unaligned(smem, p0 + l);
+            if (x) {
+                l += (__ffs(x) - 1) >> 3;
+                break;
+            }
+            l += 4;
+            a = b;
+        }
+    }
+    return min(l, max_len);
+}
+
 }  // namespace lz77

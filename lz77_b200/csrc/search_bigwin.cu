@@ -183,6 +183,24 @@ __device__ __forceinline__ int warp_lower_bound_g(const uint32_t *__restrict__ e
     return base + (m ? __ffs(m) - 1 : 32);
 }
 
+// One candidate per lane of a round.  The first four bytes are compared without a
+// branch by every lane (a lane without a candidate, `in` false, reads the target
+// itself and is masked afterwards): most candidates end there, and a divergent round
+// costs every path once.  Lanes whose first word matches go on from byte 4.
+template <bool kSmallLA>
+__device__ __forceinline__ int round_match_len_big(const uint8_t *smem, int q, bool in, int p0,
+                                                   const uint32_t (&tgt)[4], int max_len)
+{
+    const int qq = in ? q : p0;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (qq & ~3));
+    const int sh = (qq & 3) * 8;
+    const uint32_t a1 = w[1];
+    const uint32_t x = __funnelshift_r(w[0], a1, sh) ^ tgt[0];
+    int l = (int)min((uint32_t)(__ffs(x) - 1) >> 3, 4u);  // __ffs(0) - 1 wraps: 4
+    if (in && x == 0u) l = match_len_from4<kSmallLA>(smem, w, sh, a1, p0, tgt, max_len);
+    return in ? min(l, max_len) : 0;
+}
+
 constexpr int kBigWarps = 16;
 
 template <bool kSmallLA>
@@ -235,11 +253,10 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
     const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // smem index of block byte 0 (may be < 0)
     const uint32_t *blk_sorted = sorted + blk_lo;
     const uint32_t *blk_bstart = bstart + blk_i * (kBigBuckets + 1);
-    uint32_t *tok_row = tok_tmp + sgm * kSegBytes + lane;
+    uint32_t *const tok_row = tok_tmp + sgm * kSegBytes;
+    uint32_t *tok_at = tok_row;  // one 4-byte store per token by one lane (L2 merges the sectors)
     const int len_shift = P.ob, lit_shift = P.ob + P.lb;
     const int la = P.la, window = P.window;
-    int ntok = 0;
-    uint32_t held = 0;
 
     while (p0 < seg_end) {
         const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
@@ -272,20 +289,19 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                 for (; i < bn; i += 32) {
                     const int idx = i + lane;
                     const int qb = idx < bn ? (int)__ldg(e + idx) : 0x7fffffff;
-                    if (qb >= lo_blk && qb < p_blk) {
-                        const int q = qb + blk_idx;
-                        const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
-                        if (l > best_len) {
-                            best_len = l;
-                            best_q = q;
-                        }
+                    const bool in = qb >= lo_blk && qb < p_blk;
+                    const int q = qb + blk_idx;
+                    const int l = round_match_len_big<kSmallLA>(smem, q, in, p0, tgt, max_len);
+                    if (l > best_len) {  // nearer than anything this lane has seen: longer
+                        best_len = l;
+                        best_q = q;
                     }
                     if (__any_sync(0xffffffffu, best_len >= max_len || qb >= p_blk)) break;
                 }
             }
+            // (no candidate: length 0 in the top bits, the start is not used)
             const uint32_t k = __reduce_max_sync(
-                0xffffffffu,
-                best_len ? ((uint32_t)best_len << 20) | (0xfffffu - (uint32_t)best_q) : 0u);
+                0xffffffffu, ((uint32_t)best_len << 20) | (0xfffffu - (uint32_t)best_q));
             len = (int)(k >> 20);
             int q_best = (int)(0xfffffu - (k & 0xfffffu));
             if (len < 2) {
@@ -320,16 +336,11 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
 
         const uint32_t lit = smem[p0 + len];
         const uint32_t tok = (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
-        if (lane == (ntok & 31)) held = tok;
-        ntok++;
-        if ((ntok & 31) == 0) {
-            *tok_row = held;
-            tok_row += 32;
-        }
+        if (lane == 0) *tok_at = tok;
+        tok_at++;
         p0 += len + 1;
     }
-    if (lane < (ntok & 31)) *tok_row = held;
-    if (lane == 0) seg_ntok[sgm] = (uint32_t)ntok;
+    if (lane == 0) seg_ntok[sgm] = (uint32_t)(tok_at - tok_row);
 }
 
 // ---------------------------------------------------------------------------
