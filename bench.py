@@ -374,7 +374,7 @@ def run_native(args):
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "lz77_parse_kernel (longest-match search + greedy parse)",
+            "roofline": {"kernel": "lz77_parse_bucket_kernel (longest-match search + greedy parse)",
                          "bound": "hbm", "achieved": search_gbs, "peak": peak, "unit": "GB/s",
                          "frac": search_gbs / peak,
                          "traffic": ncu_traffic("lz77_parse_bucket_kernel", n),
