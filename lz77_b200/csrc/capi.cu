@@ -594,11 +594,13 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
         if (tile_end > tiles_done) {
             CK(cudaStreamWaitEvent(g.aux, ev_scan[c], 0));
             if (cross) {
-                if ((rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes()))) return rc;
+                const long long piece = decode_jump_piece(max_out, P);
+                if ((rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes(piece)))) return rc;
                 CK(launch_decode_jump_range((const uint32_t *)g.stage_in, n_in, K,
                                             tiles_done << P.tile_shift,
                                             last ? pos : tile_end << P.tile_shift, last, P,
-                                            g.scratch, g.jump, (uint8_t *)g.stage_out, g.aux));
+                                            g.scratch, g.jump, piece, (uint8_t *)g.stage_out,
+                                            g.aux));
             } else {
                 CK(launch_decode_tiles_range((const uint32_t *)g.stage_in, n_in, K, tiles_done,
                                              tile_end, last, pos, (int)c, 0, P, g.scratch,
@@ -699,9 +701,10 @@ int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_ca
     if (n == 0) return LZ77_OK;
     if (!d_out || (((uintptr_t)d_out) & 15)) return LZ77_E_ARG;
     if (out_cap < n) return LZ77_E_SPACE;
-    if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes()))) return rc;
+    const long long piece = decode_jump_piece(n, P);
+    if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes(piece)))) return rc;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
-    CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, cross, P, g.scratch, g.jump,
+    CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, cross, P, g.scratch, g.jump, piece,
                           (uint8_t *)d_out, g.stream));
     if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
     // the error flag is final only after pass 2
@@ -766,10 +769,11 @@ int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long
     if (out_cap < n) return LZ77_E_SPACE;
     rc = grow(&g.stage_out, &g.stage_out_cap, (((size_t)n + 15) & ~(size_t)15) + 16);
     if (rc) return rc;
-    if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes()))) return rc;
+    const long long piece = decode_jump_piece(n, P);
+    if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes(piece)))) return rc;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
     CK(launch_decode_copy((const uint32_t *)g.stage_in, n_in, k, n, cross, P, g.scratch, g.jump,
-                          (uint8_t *)g.stage_out, g.stream));
+                          piece, (uint8_t *)g.stage_out, g.stream));
     if (g.timing) CK(cudaEventRecord(g.ev[3], g.stream));
     CK(cudaMemcpyAsync(g.pinned, g.scratch, sizeof(DecodeInfo), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaEventRecord(g.ev[6], g.stream));

@@ -676,13 +676,13 @@ cudaError_t launch_decode_tiles_range(const uint32_t *d_in_words, long long n_in
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, long long n_out, bool cross_block,
                                const Params &P, void *scratch, void *jump_scratch,
-                               uint8_t *d_out, cudaStream_t st)
+                               long long jump_piece, uint8_t *d_out, cudaStream_t st)
 {
     // matches that leave their block (a stream of the reference encoder): the tiles
     // would form a chain, resolve the copies by pointer jumping instead
     if (cross_block)
         return launch_decode_jump_range(d_in_words, n_in_bytes, n_tokens, 0, n_out, true, P,
-                                        scratch, jump_scratch, d_out, st);
+                                        scratch, jump_scratch, jump_piece, d_out, st);
     // phase order only for streams whose matches stay inside their (multi-tile) block
     const int pair_mode = (P.block_shift > P.tile_shift && !cross_block)
                               ? P.block_shift - P.tile_shift : 0;

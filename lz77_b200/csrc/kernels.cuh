@@ -91,11 +91,13 @@ cudaError_t launch_token_at(const uint32_t *d_in_words, long long n_in_bytes, lo
 cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, long long n_out, bool cross_block,
                                const Params &P, void *scratch, void *jump_scratch,
-                               uint8_t *d_out, cudaStream_t st);
-size_t decode_jump_scratch_bytes();
+                               long long jump_piece, uint8_t *d_out, cudaStream_t st);
+long long decode_jump_piece(long long n_out_max, const Params &P);  // output bytes per round
+size_t decode_jump_scratch_bytes(long long jump_piece);
 cudaError_t launch_decode_jump_range(const uint32_t *d_in_words, long long n_in_bytes,
                                      long long n_tokens, long long out_lo, long long out_hi,
                                      bool to_end, const Params &P, void *scratch,
-                                     void *jump_scratch, uint8_t *d_out, cudaStream_t st);
+                                     void *jump_scratch, long long jump_piece, uint8_t *d_out,
+                                     cudaStream_t st);
 
 }  // namespace lz77

@@ -492,6 +492,11 @@ def test_decode_unblocked_synthetic_tokens(lz, orc, sb, la, k):
     want = orc.decode(stream)
     assert lz.decode_size(stream) == len(want)
     assert lz.decode(stream) == want
+    os.environ["LZ77_JUMP_PIECE_MIB"] = "8"  # the same in pieces of 8 MiB of output
+    try:
+        assert lz.decode(stream) == want
+    finally:
+        del os.environ["LZ77_JUMP_PIECE_MIB"]
 
 
 @pytest.mark.parametrize("sb,la", [(4095, 15), (65535, 255)])
@@ -511,8 +516,13 @@ def test_decode_unblocked_deep_chains(lz, orc, sb, la):
     lit = (np.arange(k) * 7 % 251).astype(np.int64)
     stream = _pack_tokens(off, length, lit, sb, la)
     want = orc.decode(stream)
-    assert len(want) > (36 << 20)  # more than one piece of the jump decoder
+    assert len(want) > (36 << 20)
     assert lz.decode(stream) == want
+    os.environ["LZ77_JUMP_PIECE_MIB"] = "16"  # chains that run through three pieces
+    try:
+        assert lz.decode(stream) == want
+    finally:
+        del os.environ["LZ77_JUMP_PIECE_MIB"]
 
 
 def test_decode_unblocked_after_blocked_prefix_pipelined(lz, orc):
