@@ -445,6 +445,11 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
 
 namespace {
 
+#ifndef LZ77_JUMP_WINDOW_MAX
+#define LZ77_JUMP_WINDOW_MAX 512
+#endif
+constexpr int kJumpWindowMax = LZ77_JUMP_WINDOW_MAX;  // windows up to this decode by pointer jumping
+
 // header parse, lz77.c:157-158; the header always travels through the host
 int read_header(const unsigned char hdr[4], long n_in, Params *P, long long *n_tokens)
 {
@@ -490,7 +495,10 @@ int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_toke
     CK(cudaStreamSynchronize(g.stream));
     const DecodeInfo *info = (const DecodeInfo *)g.pinned;
     *n_out = (long)info->n_out;
-    if (cross_block) *cross_block = info->cross_block != 0;
+    // Pointer jumping also for windows so small that nearly every source is still being
+    // written by a neighbouring warp of the tile decoder: it does not care
+    // how near a source is.
+    if (cross_block) *cross_block = info->cross_block != 0 || P->window <= kJumpWindowMax;
     g.last.launches = decode_launch_count(false);
     if (g.timing) g.last.dec_scan_ms = ms_between(g.ev[0], g.ev[1]);
     return LZ77_OK;
@@ -573,7 +581,8 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
         CK(cudaEventSynchronize(ev_scan[c]));
         if (g.pinned_totals[c] != ~0ull) {
             pos_seen = (long long)(g.pinned_totals[c] & ~(1ull << 63));
-            cross = (g.pinned_totals[c] >> 63) != 0;  // sticky: the flag is never cleared
+            cross = (g.pinned_totals[c] >> 63) != 0 ||  // sticky: the flag is never cleared
+                    P.window <= kJumpWindowMax;
         }
         const long long pos = pos_seen;
         const bool last = c + 1 == n_chunks;
