@@ -168,6 +168,7 @@ void lz77_gpu_shutdown(void)
     for (auto &e : g.pool) cudaEventDestroy(e);
     if (g.scratch) cudaFree(g.scratch);
     if (g.jump) cudaFree(g.jump);
+    bigwin_release();
     if (g.stage_in) cudaFree(g.stage_in);
     if (g.stage_out) cudaFree(g.stage_out);
     if (g.pinned) cudaFreeHost(g.pinned);

@@ -44,6 +44,8 @@ cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Param
                                 void *scratch, uint32_t *tok_tmp, uint32_t *seg_ntok,
                                 cudaStream_t st);
 
+void bigwin_release();  // side stream + events of the large-window encoder
+
 // ---- decoder (decode.cu) ---------------------------------------------------
 struct DecodeInfo {            // lives in device scratch, copied back by the C ABI
     unsigned long long n_out;  // decoded size

@@ -389,6 +389,19 @@ cudaError_t bigwin_streams()
 }
 }  // namespace
 
+// called by lz77_gpu_shutdown()
+void bigwin_release()
+{
+    if (g_bw.device < 0) return;
+    cudaStreamDestroy(g_bw.sort);
+    cudaEventDestroy(g_bw.fork);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(g_bw.sorted[i]);
+        cudaEventDestroy(g_bw.parsed[i]);
+    }
+    g_bw = BigwinStreams();
+}
+
 // d_in points at a block boundary.  The input is handled in pieces of kBigPiece
 // bytes: the block sort of piece k+1 runs on a high-priority side stream while
 // piece k is parsed on `st` (two sets of tables in the scratch area).
