@@ -258,6 +258,9 @@ __global__ void lz77_token_at_kernel(const uint32_t *__restrict__ words, long lo
 // pass 2: tile decode
 // ---------------------------------------------------------------------------
 
+#ifndef LZ77_DEC_PREFETCH
+#define LZ77_DEC_PREFETCH 0
+#endif
 #ifndef LZ77_DEC_SPINS
 #define LZ77_DEC_SPINS 2
 #endif
@@ -364,6 +367,14 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
         const long long g_first = k0 >> 5;
         const int n_groups = (int)(((k_end + 31) >> 5) - g_first);
         const uint32_t tile_lo32 = (uint32_t)tile_lo;
+        // token addressing relative to the tile's first group: 32-bit arithmetic per token
+        // (a tile holds at most 2^17 tokens of at most 32 bits)
+        const long long bit0 = kHeaderBits + (g_first << 5) * P.tbits;
+        const uint32_t *tile_words = words + (bit0 >> 5);
+        const int bit0_low = (int)(bit0 & 31);
+        const long long words_left = n_words - (bit0 >> 5);
+        const int n_words_rel = words_left > 0x7fffffff ? 0x7fffffff : (int)words_left;
+        const int k0_rel = (int)(k0 - (g_first << 5)), k_end_rel = (int)(k_end - (g_first << 5));
 
         for (int i = threadIdx.x; i < (tile_bytes >> 5); i += kThreads) ready_bits[i] = 0u;
         __syncthreads();
@@ -375,14 +386,30 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
             gi = __shfl_sync(0xffffffffu, gi, 0);
             if (gi >= n_groups) break;
 
-            const long long k = ((g_first + gi) << 5) + lane;
-            const bool valid = k >= k0 && k < k_end;
+            const int k = (gi << 5) + lane;  // relative to the tile's first group
+            const bool valid = k >= k0_rel && k < k_end_rel;
             uint32_t tok = 0;
-            if (k < k_end) tok = load_bits32(words, n_words, kHeaderBits + k * P.tbits);
+            if (k < k_end_rel) {
+                const int b = bit0_low + k * P.tbits;
+                const int w = b >> 5, sft = b & 31;
+                const uint32_t lo = w < n_words_rel ? __ldg(tile_words + w) : 0u;
+                const uint32_t hi = (sft != 0 && w + 1 < n_words_rel) ? __ldg(tile_words + w + 1) : 0u;
+                tok = __funnelshift_r(lo, hi, sft);
+            }
+#if LZ77_DEC_PREFETCH
+            {
+                // the tokens this warp will most likely be handed next (one group per warp
+                // and round): pull their line towards the SM while this group is decoded
+                const int kp = k + (kWarps << 5);
+                if (lane == 0 && kp < k_end_rel)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                        tile_words + ((bit0_low + kp * P.tbits) >> 5)));
+            }
+#endif
             const int off = (int)(tok & off_mask);
             const int len = (int)((tok >> P.ob) & len_mask);
             const uint32_t lit = (tok >> lit_shift) & 0xffu;
-            const int l1 = k < k_end ? len + 1 : 0;  // lanes before k0 still count in the sum
+            const int l1 = k < k_end_rel ? len + 1 : 0;  // lanes before k0 still count in the sum
             int inc = l1;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
