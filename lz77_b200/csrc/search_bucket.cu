@@ -86,70 +86,43 @@ __device__ __forceinline__ uint32_t lds8(uint32_t addr)
     return v;
 }
 
-// match_len() of match.cuh on shared addresses (sdata = shared address of the
-// staged bytes)
-template <bool kSmallLA>
-__device__ __forceinline__ int match_len_s(uint32_t sdata, int q, int p0,
-                                           const uint32_t (&tgt)[4], int max_len)
+// match_len<false>() of match.cuh on shared addresses (sdata = shared address of the
+// staged bytes): lookaheads longer than 16 bytes.  The first 16 bytes are compared with
+// the registers, the rest word by word.
+__device__ __forceinline__ int match_len_long(uint32_t sdata, int q, int p0,
+                                              const uint32_t (&tgt)[4], int max_len)
 {
     const uint32_t w = sdata + (uint32_t)(q & ~3);
     const int sh = (q & 3) * 8;
-    if (kSmallLA) {
-        const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
-        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
-        int l;
+    const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
+    uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
+    if (x) return min((__ffs(x) - 1) >> 3, max_len);
+    const uint32_t a2 = lds32(w + 8);
+    x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
+    if (x) return min(4 + ((__ffs(x) - 1) >> 3), max_len);
+    const uint32_t a3 = lds32(w + 12);
+    x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
+    if (x) return min(8 + ((__ffs(x) - 1) >> 3), max_len);
+    uint32_t a = lds32(w + 16);
+    x = __funnelshift_r(a3, a, sh) ^ tgt[3];
+    if (x) return min(12 + ((__ffs(x) - 1) >> 3), max_len);
+    int l = 16;
+    uint32_t wa = w + 20;
+    while (l < max_len) {
+        const uint32_t b = lds32(wa);
+        wa += 4;
+        const int pi = p0 + l;
+        const uint32_t pw = sdata + (uint32_t)(pi & ~3);
+        const uint32_t t = __funnelshift_r(lds32(pw), lds32(pw + 4), (pi & 3) * 8);
+        x = __funnelshift_r(a, b, sh) ^ t;
         if (x) {
-            l = (__ffs(x) - 1) >> 3;
-        } else {
-            const uint32_t a2 = lds32(w + 8);
-            x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
-            if (x) {
-                l = 4 + ((__ffs(x) - 1) >> 3);
-            } else {
-                const uint32_t a3 = lds32(w + 12);
-                x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
-                if (x) {
-                    l = 8 + ((__ffs(x) - 1) >> 3);
-                } else {
-                    const uint32_t a4 = lds32(w + 16);
-                    x = __funnelshift_r(a3, a4, sh) ^ tgt[3];
-                    l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
-                }
-            }
+            l += (__ffs(x) - 1) >> 3;
+            break;
         }
-        return min(l, max_len);
-    } else {
-        // LA > 16: first the 16 register-resident bytes, then word by word
-        const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
-        uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt[0];
-        if (x) return min((__ffs(x) - 1) >> 3, max_len);
-        const uint32_t a2 = lds32(w + 8);
-        x = __funnelshift_r(a1, a2, sh) ^ tgt[1];
-        if (x) return min(4 + ((__ffs(x) - 1) >> 3), max_len);
-        const uint32_t a3 = lds32(w + 12);
-        x = __funnelshift_r(a2, a3, sh) ^ tgt[2];
-        if (x) return min(8 + ((__ffs(x) - 1) >> 3), max_len);
-        uint32_t a = lds32(w + 16);
-        x = __funnelshift_r(a3, a, sh) ^ tgt[3];
-        if (x) return min(12 + ((__ffs(x) - 1) >> 3), max_len);
-        int l = 16;
-        uint32_t wa = w + 20;
-        while (l < max_len) {
-            const uint32_t b = lds32(wa);
-            wa += 4;
-            const int pi = p0 + l;
-            const uint32_t pw = sdata + (uint32_t)(pi & ~3);
-            const uint32_t t = __funnelshift_r(lds32(pw), lds32(pw + 4), (pi & 3) * 8);
-            x = __funnelshift_r(a, b, sh) ^ t;
-            if (x) {
-                l += (__ffs(x) - 1) >> 3;
-                break;
-            }
-            l += 4;
-            a = b;
-        }
-        return min(l, max_len);
+        l += 4;
+        a = b;
     }
+    return min(l, max_len);
 }
 
 // One candidate per lane of a round, LA <= 16.  The first four bytes are compared
@@ -219,9 +192,6 @@ __device__ __forceinline__ int group_lower_bound_s(uint32_t se, int n, int lo, i
 // parses 32 / kLanes segments side by side: the per-token scalar work (target
 // load, bucket lookup, window bound, reduction, emit) is issued once for all
 // the groups of a warp that are in step.
-#ifndef LZ77_EMIT_ROWS
-#define LZ77_EMIT_ROWS 0
-#endif
 #ifndef LZ77_PARSE_MINBLOCKS
 #define LZ77_PARSE_MINBLOCKS 1
 #endif
@@ -390,12 +360,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             uint32_t *tok_row = tok_tmp + sgm * kSegBytes;
             const int len_shift = P.ob, lit_shift = P.ob + P.lb;
             const int la = P.la, window = P.window;
-#if LZ77_EMIT_ROWS
-            int ntok = 0;
-            uint32_t held = 0;
-#else
             uint32_t *tok_at = tok_row;  // a running pointer: no address arithmetic per token
-#endif
 
             while (p0 < seg_end) {
                 const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
@@ -444,7 +409,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                                 best_q = q;
                             }
                         } else if (in) {
-                            const int l = match_len_s<false>(sdata, q, p0, tgt, max_len);
+                            const int l = match_len_long(sdata, q, p0, tgt, max_len);
                             if (l > best_len) {
                                 best_len = l;
                                 best_q = q;
@@ -494,24 +459,14 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                 const uint32_t lit = lds8(sdata + (uint32_t)(p0 + len));
                 const uint32_t tok =
                     (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
-#if LZ77_EMIT_ROWS
-                if (sl == (ntok & (kLanes - 1))) held = tok;
-                ntok++;
-                if ((ntok & (kLanes - 1)) == 0) {  // a full row: one coalesced store
-                    tok_row[ntok - kLanes + sl] = held;
-                }
-                p0 += len + 1;
-            }
-            if (sl < (ntok & (kLanes - 1))) tok_row[(ntok & ~(kLanes - 1)) + sl] = held;
-#else
                 // one 4-byte store per token by one lane: fewer instructions than
-                // collecting rows of 32 tokens in registers, and L2 merges the sectors
+                // collecting rows of 32 tokens in registers (measured 9.6 -> 9.4 ms), and
+                // L2 merges the sectors
                 if (sl == 0) *tok_at = tok;
                 tok_at++;
                 p0 += len + 1;
             }
             const int ntok = (int)(tok_at - tok_row);
-#endif
             if (sl == 0) seg_ntok[sgm] = (uint32_t)ntok;
         }
         __syncthreads();  // the next tile overwrites the staged data and the buckets
