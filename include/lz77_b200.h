@@ -85,7 +85,8 @@ const char *lz77_gpu_last_error(void);
 int  lz77_gpu_set_stream(void *cuda_stream);
 
 /* The host entry points pipeline inputs larger than this many bytes in chunks
- * (H2D copy, kernels and D2H copy of successive chunks overlap; default 16 MiB).
+ * (H2D copy, kernels and D2H copy of successive chunks overlap; default 8 MiB,
+ * 16 MiB for windows above 8191 bytes).
  * bytes <= 0 turns chunking off. */
 void lz77_gpu_set_host_chunk(long bytes);
 

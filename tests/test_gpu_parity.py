@@ -216,7 +216,7 @@ def test_cli_cross_roundtrip_with_reference(lz, orc, tmp_path):
 @pytest.mark.parametrize("sb,la,n", [(4095, 15, 80 << 20), (1000, 20, (70 << 20) + 12_345),
                                      (4095, 15, (64 << 20) + 3), (1, 2, (33 << 20) + 1)])
 def test_host_chunked_encode_equals_device_encode(lz, orc, sb, la, n):
-    """The host entry point pipelines inputs above 16 MiB in chunks (H2D, kernels
+    """The host entry point pipelines inputs above 8 / 16 MiB in chunks (H2D, kernels
     and D2H overlapped); the stream must be bit-identical to the one-shot device
     encode, also when a chunk seam falls inside a byte (23- and 9-bit tokens)."""
     import torch
@@ -432,7 +432,7 @@ def test_compressed_size_close_to_reference(lz, orc, kind, sb, la, tol):
 @pytest.mark.parametrize("sb,la", [(4095, 15), (1000, 20), (65535, 255)])
 @pytest.mark.parametrize("n", [(16 << 20) + 1, (32 << 20) - 1, (48 << 20) + 123_457])
 def test_host_pipeline_chunk_seams(lz, sb, la, n):
-    """Inputs that end just past / just before a 16 MiB host chunk: the pipelined
+    """Inputs that end just past / just before a host chunk (8 or 16 MiB): the pipelined
     host encode must equal the one-shot device encode bit for bit, and the
     pipelined host decode must return the input."""
     import torch

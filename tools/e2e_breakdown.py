@@ -18,7 +18,7 @@ src = synth.zipf_text(n, seed=1234, device="cuda")
 cap = api.encode_bound(n) + 16
 h_in, h_stream, h_out = api.PinnedBuffer(n), api.PinnedBuffer(cap), api.PinnedBuffer(n + 16)
 h_in.array[:] = src.cpu().numpy()
-for chunk_mib in (0, 8, 16, 32, 64):
+for chunk_mib in (0, 4, 8, 12, 16, 24, 32):
     api.set_host_chunk(chunk_mib << 20)
     for _ in range(2):
         c = api.encode_into(h_in.ptr, n, h_stream.ptr, cap)
