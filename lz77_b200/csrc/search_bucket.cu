@@ -398,7 +398,12 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
                                 : group_lower_bound_s<kLanes>(se, bn, lo_idx, sl, gmask, gshift);
                     for (; i < bn; i += kLanes) {
                         const int idx = i + sl;
-                        const int q = idx < bn ? (int)lds16(se + 2u * idx) : 0x7fffffff;
+                        // LA <= 16: the last round of a bucket reads on into the next one (or the
+                        // padding behind the list).  Whatever turns up there is only accepted as
+                        // an in-window position whose bytes really match, and such a position with
+                        // two or more matching bytes is in this bucket anyway; a one-byte match is
+                        // rescanned below.  Saves the bounds predicate in every round.
+                        const int q = (kSmallLA || idx < bn) ? (int)lds16(se + 2u * idx) : 0x7fffffff;
                         const bool in = q >= lo_idx && q < p0;
                         if (kSmallLA) {
                             const int l = round_match_len(sdata, q, in, p0, tgt[0], tgt[1], tgt[2], tgt[3],
@@ -495,7 +500,7 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Param
     size_t smem = (data_cap + 15) & ~(size_t)15;               // staged bytes
     smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // bucket starts
     smem += (size_t)kBuckets * (kW / 2) * 4;                   // per-warp counters
-    smem += data_cap * sizeof(uint16_t) + 16;                  // sorted positions
+    smem += data_cap * sizeof(uint16_t) + 80;                  // sorted positions + one round of padding
     auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, kL, uint16_t, false>
                          : lz77_parse_bucket_kernel<false, kW, kL, uint16_t, false>;
     cudaError_t rc =
