@@ -69,6 +69,27 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_near_gpu(local_rank: int) -> None:
+    """One process per GPU: run on the CPUs next to this rank's GPU, so that the pinned
+    host buffers of the end-to-end leg are allocated on the GPU's NUMA node (with several
+    ranks on one socket's memory the H2D / D2H copies share its bandwidth).  Best effort:
+    any failure leaves the affinity as it was."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] no NUMA binding for rank {local_rank}: {e}", file=sys.stderr)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -240,6 +261,8 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this codec has no CPU path")
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        bind_near_gpu(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
