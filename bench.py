@@ -250,6 +250,103 @@ def run_reference(args):
 # this framework
 # --------------------------------------------------------------------------- #
 
+def sharded_workload(world: int):
+    """ONE input resident on rank 0, cut into runs of whole blocks over all ranks (NCCL
+    scatter -> per-rank encode -> gather into ONE stream -> sharded decode)."""
+    if world == 4:   # BASELINE.json configs[3]
+        return dict(name="configs[3]: 4 GiB log-like (4 KiB period), -s 4095 -l 15, 4 GPUs",
+                    kind="log_like", n=4 << 30, sb=4095, la=15, seed=1234)
+    if world == 8:   # configs[4]'s generator and parameters, 1 GiB per GPU: the worst-case
+        #              stream bound of the full 32 GiB (128 GiB) does not fit root's HBM
+        return dict(name="configs[4] generator: 8 GiB mixed corpus, -s 65535 -l 255, 8 GPUs",
+                    kind="mixed", n=8 << 30, sb=65535, la=255, seed=1234)
+    return dict(name=f"{world} x 256 MiB synthetic Zipf text, -s 4095 -l 15",
+                kind="zipf_text", n=world * (256 << 20), sb=4095, la=15, seed=1234)
+
+
+def run_sharded(args, dist, dev, rank, world, barrier):
+    """Returns the `sharded` record (rank 0) -- timed with CUDA events around the
+    collective calls, max over ranks; the NCCL transfers are inside the timed region."""
+    import hashlib
+    import torch
+    import lz77_b200
+    from lz77_b200 import api, synth
+
+    wl = sharded_workload(world)
+    if args.sharded_bytes:
+        wl = dict(wl, n=args.sharded_bytes, name=wl["name"] + f" (cut to {args.sharded_bytes} B)")
+    n, sb, la = wl["n"], wl["sb"], wl["la"]
+    api.comm_init_torch(dev)
+    src = out_stream = out_plain = None
+    if rank == 0:
+        src = synth.make(wl["kind"], n, seed=wl["seed"], device=dev)
+        cap = (api.encode_bound(n, sb, la) + 15) & ~15
+        out_stream = torch.empty(cap, dtype=torch.uint8, device=dev)
+        out_plain = torch.empty((n + 15) & ~15, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, args.sharded_steps))
+    stream_t = torch.cuda.current_stream(dev)
+    merged = back = None
+    for _ in range(2):   # warm-up: allocations, NCCL channels
+        merged, k = api.encode_sharded_tensor(src, la=la, sb=sb, out=out_stream)
+        back = api.decode_sharded_tensor(merged, out=out_plain)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    enc_stats, dec_stats = [], []
+    barrier()
+    ev[0].record(stream_t)
+    for i in range(steps):
+        merged, k = api.encode_sharded_tensor(src, la=la, sb=sb, out=out_stream)
+        enc_stats.append(api.comm_stats())
+        ev[2 * i + 1].record(stream_t)
+        back = api.decode_sharded_tensor(merged, out=out_plain)
+        dec_stats.append(api.comm_stats())
+        ev[2 * i + 2].record(stream_t)
+    barrier()
+    enc_ms = sum(ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)) / steps
+    dec_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)) / steps
+    times = torch.tensor([enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    enc_ms, dec_ms = times.tolist()
+    rec = None
+    if rank == 0:
+        # bit identity: the merged stream against what ONE GPU writes for the whole input
+        roundtrip = bool(torch.equal(back, src))
+        del out_plain, back
+        single, k1 = lz77_b200.encode_tensor(src, la=la, sb=sb)
+        same = bool(single.numel() == merged.numel() and torch.equal(single, merged) and k1 == k)
+        sha_m = hashlib.sha256(merged.cpu().numpy()).hexdigest()
+        sha_s = hashlib.sha256(single.cpu().numpy()).hexdigest()
+        med = lambda rows, key: statistics.median(r[key] for r in rows)  # noqa: E731
+        nv_enc = enc_stats[-1]["sent_bytes"] + enc_stats[-1]["recv_bytes"]
+        nv_dec = dec_stats[-1]["sent_bytes"] + dec_stats[-1]["recv_bytes"]
+        phases = {"enc_scatter_ms": med(enc_stats, "scatter_ms"),
+                  "enc_compute_ms_root": med(enc_stats, "compute_ms"),
+                  "enc_gather_ms": med(enc_stats, "gather_ms"),
+                  "dec_scatter_ms": med(dec_stats, "scatter_ms"),
+                  "dec_compute_ms_root": med(dec_stats, "compute_ms"),
+                  "dec_gather_ms": med(dec_stats, "gather_ms")}
+        worst = max(("enc_scatter_ms", "enc_gather_ms", "dec_scatter_ms", "dec_gather_ms"),
+                    key=lambda k_: phases[k_])
+        names = {"enc_scatter_ms": "scatter of the input runs (grouped ncclSend/ncclRecv, root -> ranks)",
+                 "enc_gather_ms": "gather of the token payloads (grouped ncclSend/ncclRecv, ranks -> root)",
+                 "dec_scatter_ms": "scatter of the token slices (grouped ncclSend/ncclRecv, root -> ranks)",
+                 "dec_gather_ms": "gather of the plaintext (grouped ncclSend/ncclRecv, ranks -> root)"}
+        rec = {"workload": wl["name"], "bytes": n, "ranks": world, "steps": steps,
+               "bit_identical": same and sha_m == sha_s, "roundtrip_exact": roundtrip,
+               "sha256": sha_m, "stream_bytes": int(merged.numel()), "tokens": int(k),
+               "gbs": n / ((enc_ms + dec_ms) * 1e-3) / 1e9,
+               "encode_gbs": n / (enc_ms * 1e-3) / 1e9, "decode_gbs": n / (dec_ms * 1e-3) / 1e9,
+               "encode_ms": enc_ms, "decode_ms": dec_ms,
+               "nvlink_bytes": int(nv_enc + nv_dec),
+               "nvlink_bytes_encode": int(nv_enc), "nvlink_bytes_decode": int(nv_dec),
+               "phases_ms": phases, "limiting_collective": names[worst],
+               "transport": "NCCL point-to-point inside liblz77b200.so (comm.cu), one rank per GPU"}
+        assert rec["bit_identical"], "sharded stream differs from the single-GPU stream"
+        assert roundtrip, "sharded roundtrip mismatch"
+    api.comm_destroy()
+    return rec
+
+
 def run_native(args):
     import torch
     import lz77_b200
@@ -371,6 +468,13 @@ def run_native(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     total_ms, enc_ms, dec_ms, e2e_ms = times.tolist()
 
+    sharded = None
+    if dist is not None and not args.no_sharded:
+        del src, stream_buf, out_buf, s, back
+        h_in.free(), h_stream.free(), h_out.free()
+        torch.cuda.empty_cache()
+        sharded = run_sharded(args, dist, dev, rank, world, barrier)
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         med = {k_: statistics.median(v) for k_, v in per.items()}
@@ -409,7 +513,9 @@ def run_native(args):
                                 "traffic": ncu_traffic("lz77_decode_tile_kernel", n),
                                 "algorithmic_bytes": alg_bytes},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if sharded is not None:
+            line["sharded"] = sharded
+        if not args.no_cpu_baseline:
             try:
                 ref = CpuReference(slice_bytes=args.ref_slice_mib << 20)
                 dt, b, c_ref = ref.step()
@@ -436,6 +542,10 @@ def main():
     ap.add_argument("--ref-slice-mib", type=int, default=8,
                     help="per-core slice the CPU reference encodes+decodes per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="N > 1: skip the one-input sharded leg (NCCL scatter/gather)")
+    ap.add_argument("--sharded-steps", type=int, default=3)
+    ap.add_argument("--sharded-bytes", type=int, default=0, help="override the sharded input size")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":

@@ -28,9 +28,11 @@
  * Conventions: plain pointers and sizes; the caller owns every buffer; every
  * entry point returns 0 or a negative LZ77_E_* code and never calls exit();
  * there is NO CPU fallback -- without a CUDA device every compute entry point
- * returns LZ77_E_NODEVICE.  One host thread drives one GPU (one process per
- * GPU for multi-GPU runs); calls are synchronous (the result is complete on
- * return).  Not re-entrant on the same device from several threads.
+ * returns LZ77_E_NODEVICE.  One host thread drives one GPU: lz77_gpu_init()
+ * binds the calling thread to a device, and the state of every device is its
+ * own, so several threads (or several processes) drive several GPUs side by
+ * side.  Calls are synchronous (the result is complete on return).  Not
+ * re-entrant on the same device from several threads.
  */
 #ifndef LZ77_B200_H
 #define LZ77_B200_H
@@ -54,6 +56,7 @@ extern "C" {
 #define LZ77_E_NOMEM    (-4)  /* host or device allocation failed                 */
 #define LZ77_E_NODEVICE (-5)  /* no CUDA device / library not initialised         */
 #define LZ77_E_CUDA     (-6)  /* a CUDA call failed; see lz77_gpu_last_error()    */
+#define LZ77_E_COMM     (-7)  /* NCCL failed / no communicator; lz77_gpu_last_error() */
 
 /* ---- format arithmetic (host only, no device needed) -------------------- */
 
@@ -72,9 +75,12 @@ long lz77_gpu_segment_size(void);
 /* ---- lifetime ------------------------------------------------------------ */
 
 int  lz77_gpu_device_count(void);
-/* bind the library to one CUDA device (creates its stream and scratch).
- * Calling it again with another device re-binds. */
+/* Bind the calling thread to one CUDA device (creates the device's stream and
+ * scratch on first use).  Calling it again with another device re-binds the
+ * thread; the state of the first device stays alive.  Threads that never
+ * called it use the device of the most recent call. */
 int  lz77_gpu_init(int device);
+/* releases the state of every device; no other thread may be in the library */
 void lz77_gpu_shutdown(void);
 const char *lz77_gpu_strerror(int rc);
 const char *lz77_gpu_last_error(void);
@@ -89,6 +95,12 @@ int  lz77_gpu_set_stream(void *cuda_stream);
  * 16 MiB for windows above 8191 bytes).
  * bytes <= 0 turns chunking off. */
 void lz77_gpu_set_host_chunk(long bytes);
+
+/* Streams the reference encoder wrote (matches that leave their block) are
+ * decoded by pointer jumping over pieces of this many output bytes (default
+ * 64 MiB, 1 MiB .. 256 MiB; the scratch is 12 bytes per byte of a piece).
+ * 0 restores the default. */
+int lz77_gpu_set_jump_piece(long bytes);
 
 /* pinned host memory for fast host<->device copies (optional) */
 void *lz77_gpu_host_alloc(long n);
@@ -126,6 +138,67 @@ int lz77_gpu_slice_tokens_device(const void *d_in, long n_in, long tok_lo, long 
                                  void *d_out, long out_cap, long *n_out);
 int lz77_gpu_token_at_device(const void *d_in, long n_in, long pos,
                              long *tok, long *tok_pos);
+
+/* ---- several GPUs: one input, one stream ----------------------------------
+ * The encoder's blocks are independent (no reference counterpart: the reference
+ * is one sequential loop, lz77.c:89-135), so a run of whole blocks can be encoded
+ * on any GPU and the token payloads of consecutive runs concatenate into exactly
+ * the stream one GPU writes for the whole input: one header (lz77.c:74-75), then
+ * fixed-width tokens back to back (lz77.c:246-252).  Ranks are one per GPU --
+ * processes (torchrun, MPI) or threads of one process -- joined by an NCCL
+ * communicator the library owns: rank 0 obtains an id, every rank passes the
+ * same id to lz77_comm_init() after lz77_gpu_init(its device).
+ *
+ *   encode_sharded  scatter of block runs from root (grouped ncclSend/ncclRecv
+ *                   over NVLink) -> every rank encodes its run -> all-gather of
+ *                   the token counts -> the payloads travel to root, straight to
+ *                   their byte offset when T is a multiple of 8, through a
+ *                   device-side bit shift (<= 7-bit seam merge) otherwise
+ *   decode_sharded  tokens are fixed width, so root cuts the token array evenly
+ *                   (plus one block of margin) without parsing -> every rank sums
+ *                   len+1 over its tokens -> all-gather -> every rank finds the
+ *                   token that starts the first block at or after its position ->
+ *                   all-gather of these split points -> every rank decodes its
+ *                   run of whole blocks -> the plaintext travels to root.  Only
+ *                   streams of the block encoder shard; a stream of the
+ *                   reference encoder is LZ77_E_STREAM on every rank (replicas
+ *                   only: each GPU would need its predecessor's last SB bytes).
+ *
+ * Both are collective: every rank of the communicator calls them; d_in / d_out /
+ * n_in / sb / la / out_cap count on root only (device pointers, 16-byte aligned).
+ * Every rank returns the same code; n_out / n_tokens are set on every rank. */
+#define LZ77_COMM_ID_BYTES 128
+/* byte range [*lo, *hi) of rank `rank` of `world`: contiguous runs of whole
+ * blocks, as even as whole blocks allow (host only, no device needed) */
+int lz77_shard_range(long n_bytes, int world, long block, int rank, long *lo, long *hi);
+int lz77_comm_get_unique_id(void *id /* LZ77_COMM_ID_BYTES */);
+int lz77_comm_init(const void *id, int rank, int world);
+void lz77_comm_destroy(void);
+int lz77_gpu_encode_sharded_device(const void *d_in, long n_in, int sb, int la,
+                                   void *d_out, long out_cap,
+                                   long *n_out, long *n_tokens, int root);
+int lz77_gpu_decode_sharded_device(const void *d_in, long n_in,
+                                   void *d_out, long out_cap, long *n_out, int root);
+/* what the last sharded call of this rank moved through the communicator */
+struct lz77_comm_stats {
+    long  sent_bytes, recv_bytes;  /* payload bytes this rank sent / received    */
+    float scatter_ms;              /* input (encode) / token slices (decode)     */
+    float compute_ms;              /* this rank's kernels                        */
+    float gather_ms;               /* payloads (encode) / plaintext (decode)     */
+    float total_ms;
+    int   collectives;             /* NCCL calls (groups count once)             */
+};
+int lz77_comm_last_stats(struct lz77_comm_stats *s);
+
+/* Single process, n_gpus devices (what the command-line program's -G uses): the
+ * library keeps one worker thread per device, each a rank of its own
+ * communicator.  Host buffers; root = device 0 copies them in and out. */
+int  lz77_mgpu_init(int n_gpus);
+void lz77_mgpu_shutdown(void);
+int  lz77_mgpu_encode(const unsigned char *in, long n_in, int sb, int la,
+                      unsigned char *out, long out_cap, long *n_out);
+int  lz77_mgpu_decode(const unsigned char *in, long n_in,
+                      unsigned char *out, long out_cap, long *n_out);
 
 /* ---- measurement ---------------------------------------------------------
  * Device time (CUDA events on the library's stream) of each kernel of the

@@ -18,7 +18,8 @@ LIB_PATH = Path(os.environ.get("LZ77_B200_LIB", _HERE / "liblz77b200.so"))  # ov
 DEFAULT_LA = 15    # reference lz77.c:21
 DEFAULT_SB = 4095  # reference lz77.c:22
 
-E_ARG, E_SPACE, E_STREAM, E_NOMEM, E_NODEVICE, E_CUDA = -1, -2, -3, -4, -5, -6
+E_ARG, E_SPACE, E_STREAM, E_NOMEM, E_NODEVICE, E_CUDA, E_COMM = -1, -2, -3, -4, -5, -6, -7
+COMM_ID_BYTES = 128
 
 # every symbol include/lz77_b200.h declares
 EXPORTS = (
@@ -28,7 +29,10 @@ EXPORTS = (
     "lz77_gpu_encode", "lz77_gpu_decode_size", "lz77_gpu_decode", "lz77_gpu_encode_device",
     "lz77_gpu_decode_size_device", "lz77_gpu_decode_device", "lz77_gpu_last_timing",
     "lz77_gpu_set_timing", "lz77_gpu_set_stream", "lz77_gpu_set_host_chunk",
-    "lz77_gpu_slice_tokens_device", "lz77_gpu_token_at_device",
+    "lz77_gpu_slice_tokens_device", "lz77_gpu_token_at_device", "lz77_gpu_set_jump_piece",
+    "lz77_shard_range", "lz77_comm_get_unique_id", "lz77_comm_init", "lz77_comm_destroy",
+    "lz77_gpu_encode_sharded_device", "lz77_gpu_decode_sharded_device", "lz77_comm_last_stats",
+    "lz77_mgpu_init", "lz77_mgpu_shutdown", "lz77_mgpu_encode", "lz77_mgpu_decode",
 )
 
 
@@ -44,6 +48,17 @@ class Timing(C.Structure):
         ("dec_scan_ms", C.c_float), ("dec_copy_ms", C.c_float),
         ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
         ("launches", C.c_int), ("n_tokens", C.c_long),
+    ]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class CommStats(C.Structure):
+    _fields_ = [
+        ("sent_bytes", C.c_long), ("recv_bytes", C.c_long), ("scatter_ms", C.c_float),
+        ("compute_ms", C.c_float), ("gather_ms", C.c_float), ("total_ms", C.c_float),
+        ("collectives", C.c_int),
     ]
 
     def as_dict(self) -> dict:
@@ -91,6 +106,18 @@ def load_library() -> C.CDLL:
         "lz77_gpu_set_host_chunk": (None, [lp]),
         "lz77_gpu_slice_tokens_device": (ip, [vp, lp, lp, lp, vp, lp, plong]),
         "lz77_gpu_token_at_device": (ip, [vp, lp, lp, plong, plong]),
+        "lz77_gpu_set_jump_piece": (ip, [lp]),
+        "lz77_shard_range": (ip, [lp, ip, lp, ip, plong, plong]),
+        "lz77_comm_get_unique_id": (ip, [vp]),
+        "lz77_comm_init": (ip, [vp, ip, ip]),
+        "lz77_comm_destroy": (None, []),
+        "lz77_gpu_encode_sharded_device": (ip, [vp, lp, ip, ip, vp, lp, plong, plong, ip]),
+        "lz77_gpu_decode_sharded_device": (ip, [vp, lp, vp, lp, plong, ip]),
+        "lz77_comm_last_stats": (ip, [C.POINTER(CommStats)]),
+        "lz77_mgpu_init": (ip, [ip]),
+        "lz77_mgpu_shutdown": (None, []),
+        "lz77_mgpu_encode": (ip, [vp, lp, ip, ip, vp, lp, plong]),
+        "lz77_mgpu_decode": (ip, [vp, lp, vp, lp, plong]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -104,8 +131,10 @@ def _check(rc: int) -> None:
     if rc != 0:
         lib = load_library()
         msg = lib.lz77_gpu_strerror(rc).decode()
-        if rc == E_CUDA:
-            msg += ": " + lib.lz77_gpu_last_error().decode()
+        if rc in (E_CUDA, E_COMM, E_STREAM):
+            detail = lib.lz77_gpu_last_error().decode()
+            if detail:
+                msg += ": " + detail
         raise Lz77Error(rc, msg)
 
 
@@ -175,6 +204,11 @@ def set_host_chunk(nbytes: int) -> None:
 
 def set_timing(enabled: bool) -> None:
     load_library().lz77_gpu_set_timing(1 if enabled else 0)
+
+
+def set_jump_piece(nbytes: int) -> None:
+    """Output bytes per piece of the pointer-jumping decoder (0: the default, 64 MiB)."""
+    _check(load_library().lz77_gpu_set_jump_piece(nbytes))
 
 
 # ---- host buffers: the call a user of the reference makes ---------------------
@@ -348,3 +382,121 @@ def decode_tensor(stream, out=None):
     _check(lib.lz77_gpu_decode_device(stream.data_ptr(), stream.numel(), out.data_ptr(),
                                       out.numel(), C.byref(m)))
     return out[:m.value]
+
+
+# ---- several GPUs: one input, one stream (NCCL inside the library) -------------
+
+def shard_range(n_bytes: int, world: int, block: int, rank: int):
+    """Byte range [lo, hi) of `rank`: a contiguous run of whole blocks (host arithmetic)."""
+    lo, hi = C.c_long(0), C.c_long(0)
+    _check(load_library().lz77_shard_range(n_bytes, world, block, rank, C.byref(lo), C.byref(hi)))
+    return lo.value, hi.value
+
+
+def comm_unique_id() -> bytes:
+    """The id rank 0 hands to every rank (any transport) before ``comm_init``."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(load_library().lz77_comm_get_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(uid: bytes, rank: int, world: int) -> None:
+    """Join the library's NCCL communicator (after ``init(device)``)."""
+    assert len(uid) == COMM_ID_BYTES
+    buf = C.create_string_buffer(uid, COMM_ID_BYTES)
+    _check(load_library().lz77_comm_init(buf, rank, world))
+
+
+def comm_init_torch(device) -> None:
+    """``comm_init`` with the id carried by torch.distributed's default group."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    init(device.index)
+    t = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    comm_init(bytes(t.cpu().numpy()), rank, world)
+
+
+def comm_destroy() -> None:
+    if _lib is not None:
+        _lib.lz77_comm_destroy()
+
+
+def comm_stats() -> dict:
+    s = CommStats()
+    _check(load_library().lz77_comm_last_stats(C.byref(s)))
+    return s.as_dict()
+
+
+def encode_sharded_tensor(src, n_in: int = 0, la: int = -1, sb: int = -1, out=None, root: int = 0):
+    """Collective: every rank calls it; on root `src` is the whole input (CUDA uint8) and
+    the result is (merged stream view, total tokens); the other ranks pass ``None`` and
+    get (None, total tokens)."""
+    import torch
+    lib = load_library()
+    n, k = C.c_long(0), C.c_long(0)
+    if src is not None:
+        assert src.is_cuda and src.dtype == torch.uint8 and src.is_contiguous()
+        n_in = src.numel()
+        cap = _round16(lib.lz77_gpu_encode_bound(n_in, sb, la))
+        if out is None:
+            out = torch.empty(cap, dtype=torch.uint8, device=src.device)
+        torch.cuda.current_stream(src.device).synchronize()
+        _check(lib.lz77_gpu_encode_sharded_device(src.data_ptr(), n_in, sb, la, out.data_ptr(),
+                                                  out.numel(), C.byref(n), C.byref(k), root))
+        return out[:n.value], k.value
+    _check(lib.lz77_gpu_encode_sharded_device(None, 0, sb, la, None, 0, C.byref(n), C.byref(k),
+                                              root))
+    return None, k.value
+
+
+def decode_sharded_tensor(stream, out=None, out_cap: int = 0, root: int = 0):
+    """Collective: root passes the stream (CUDA uint8) and an output tensor (or `out_cap`
+    bytes to allocate); returns the decoded view on root, None elsewhere."""
+    import torch
+    lib = load_library()
+    m = C.c_long(0)
+    if stream is not None:
+        assert stream.is_cuda and stream.dtype == torch.uint8 and stream.is_contiguous()
+        if out is None:
+            out = torch.empty(_round16(max(out_cap, 16)), dtype=torch.uint8, device=stream.device)
+        torch.cuda.current_stream(stream.device).synchronize()
+        _check(lib.lz77_gpu_decode_sharded_device(stream.data_ptr(), stream.numel(), out.data_ptr(),
+                                                  out.numel(), C.byref(m), root))
+        return out[:m.value]
+    _check(lib.lz77_gpu_decode_sharded_device(None, 0, None, 0, C.byref(m), root))
+    return None
+
+
+def mgpu_init(n_gpus: int) -> None:
+    _check(load_library().lz77_mgpu_init(n_gpus))
+
+
+def mgpu_shutdown() -> None:
+    if _lib is not None:
+        _lib.lz77_mgpu_shutdown()
+
+
+def mgpu_encode(data, la: int = -1, sb: int = -1) -> bytes:
+    """One process, every GPU of ``mgpu_init``: host buffer in, merged stream out."""
+    import numpy as np
+    lib = load_library()
+    src = _as_u8(data)
+    cap = lib.lz77_gpu_encode_bound(src.size, sb, la) + 16
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_long(0)
+    _check(lib.lz77_mgpu_encode(src.ctypes.data, src.size, sb, la, out.ctypes.data, cap, C.byref(n)))
+    return out[:n.value].tobytes()
+
+
+def mgpu_decode(stream, n_out_max: int) -> bytes:
+    import numpy as np
+    lib = load_library()
+    src = _as_u8(stream)
+    out = np.empty(max(n_out_max, 1) + 16, dtype=np.uint8)
+    m = C.c_long(0)
+    _check(lib.lz77_mgpu_decode(src.ctypes.data, src.size, out.ctypes.data, out.size, C.byref(m)))
+    return out[:m.value].tobytes()

@@ -12,77 +12,37 @@
 
 #include <vector>
 
-#include "../../include/lz77_b200.h"
-#include "kernels.cuh"
+#include <atomic>
+#include <mutex>
+
+#include "context.cuh"
 
 using namespace lz77;
 
+namespace lz77 {
+
 namespace {
+Context g_ctx[kMaxDevices + 1];            // [kMaxDevices]: the placeholder before any init
+std::atomic<Context *> g_default{nullptr};  // last context initialised by any thread
+thread_local Context *t_ctx = nullptr;      // the calling thread's binding
+std::mutex g_init_mutex;
+}  // namespace
 
-struct Context {
-    bool ready = false;
-    int device = -1;
-    cudaStream_t stream = nullptr;      // the stream every call uses
-    cudaStream_t own_stream = nullptr;  // created by init; used unless the caller sets one
-    cudaStream_t copy_in = nullptr;     // H2D / D2H streams of the chunked host path
-    cudaStream_t copy_out = nullptr;
-    cudaStream_t aux = nullptr;         // extra compute streams of the chunked host paths
-    cudaStream_t aux2 = nullptr;
-    cudaStream_t hi = nullptr;          // high-priority stream for the short kernels of a pipeline
-    unsigned long long *pinned_totals = nullptr;  // running count per host chunk, written by the
-    unsigned long long *pinned_totals_dev = nullptr;  // kernels through this device alias
-    std::vector<cudaEvent_t> pool;      // untimed events of the chunked host paths (reused)
-    void *scratch = nullptr;
-    size_t scratch_cap = 0;
-    void *jump = nullptr;  // pointer-jumping state of the cross-block decoder
-    size_t jump_cap = 0;
-    void *stage_in = nullptr;   // device staging for the host entry points
-    size_t stage_in_cap = 0;
-    void *stage_out = nullptr;
-    size_t stage_out_cap = 0;
-    unsigned long long *pinned = nullptr;  // small pinned read-back area
-    cudaEvent_t ev[8];
-    bool timing = true;
-    lz77_timing last;
-    char err[256];
-};
-
-Context g;
-
-long long kHostChunkBytes = 0;  // host entry points pipeline in chunks of this size; 0: default
-// default chunk, measured on the bench workload (encode + decode end to end): 4 / 8 / 16 / 32 MiB
-// -> 17.5 / 15.9 / 16.2 / 16.9 ms; the large-window encoder wants more blocks per launch
-long long host_chunk_bytes(const Params &P)
+Context &ctx()
 {
-    if (kHostChunkBytes != 0) return kHostChunkBytes;
-    return P.window > 8191 ? (16ll << 20) : (8ll << 20);
+    if (t_ctx) return *t_ctx;
+    Context *d = g_default.load(std::memory_order_acquire);
+    return d ? *d : g_ctx[kMaxDevices];
 }
-constexpr long long kMaxHostChunks = 4096;
 
 int fail_cuda(cudaError_t rc, const char *what)
 {
-    snprintf(g.err, sizeof g.err, "%s: %s", what, cudaGetErrorString(rc));
+    Context &c = ctx();
+    snprintf(c.err, sizeof c.err, "%s: %s", what, cudaGetErrorString(rc));
     cudaGetLastError();  // clear the sticky-free error
     if (rc == cudaErrorMemoryAllocation) return LZ77_E_NOMEM;
     if (rc == cudaErrorNoDevice || rc == cudaErrorInsufficientDriver) return LZ77_E_NODEVICE;
     return LZ77_E_CUDA;
-}
-
-#define CK(call)                                          \
-    do {                                                  \
-        cudaError_t rc_ = (call);                         \
-        if (rc_ != cudaSuccess) return fail_cuda(rc_, #call); \
-    } while (0)
-
-// the first n events of the pool (created on demand, destroyed at shutdown)
-cudaEvent_t *pool_events(size_t n)
-{
-    while (g.pool.size() < n) {
-        cudaEvent_t e;
-        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-        g.pool.push_back(e);
-    }
-    return g.pool.data();
 }
 
 int grow(void **buf, size_t *cap, size_t need)
@@ -132,6 +92,62 @@ float ms_between(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+// header parse, lz77.c:157-158; the header always travels through the host
+int read_header(const unsigned char hdr[4], long n_in, Params *P, long long *n_tokens)
+{
+    if (n_in < 4) return LZ77_E_STREAM;
+    const int sb = hdr[0] | (hdr[1] << 8);
+    const int la = hdr[2] | (hdr[3] << 8);
+    if (sb < 1 || la < 1 || la > LZ77_MAX_LA) return LZ77_E_STREAM;  // bitof(0) is undefined
+    if (make_params(sb, la, P) != LZ77_OK) return LZ77_E_STREAM;
+    // lz77.c:271-280: a short read ends the stream, so trailing bits < T are padding
+    *n_tokens = ((long long)(n_in - 4) * 8) / P->tbits;
+    return LZ77_OK;
+}
+
+}  // namespace lz77
+
+#define g (lz77::ctx())
+
+namespace {
+
+// default chunk of the pipelined host entry points, measured on the bench workload
+// (encode + decode end to end): 4 / 8 / 16 / 32 MiB -> 17.5 / 15.9 / 16.2 / 16.9 ms; the
+// large-window encoder wants more blocks per launch
+long long host_chunk_bytes(const Params &P)
+{
+    if (g.host_chunk != 0) return g.host_chunk;
+    return P.window > 8191 ? (16ll << 20) : (8ll << 20);
+}
+
+// Every exit of a pipelined host path -- also an error return in the middle of it -- first
+// waits for the asynchronous copies that read or write the caller's buffers.
+struct StreamDrain {
+    Context &c;
+    explicit StreamDrain(Context &ctx_) : c(ctx_) {}
+    ~StreamDrain()
+    {
+        cudaStreamSynchronize(c.copy_in);
+        cudaStreamSynchronize(c.copy_out);
+        cudaStreamSynchronize(c.aux);
+        cudaStreamSynchronize(c.aux2);
+        cudaStreamSynchronize(c.hi);
+        cudaStreamSynchronize(c.stream);
+    }
+};
+
+// the first n events of the pool (created on demand, destroyed at shutdown)
+cudaEvent_t *pool_events(size_t n)
+{
+    Context &c = g;
+    while (c.pool.size() < n) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        c.pool.push_back(e);
+    }
+    return c.pool.data();
+}
+
 }  // namespace
 
 extern "C" {
@@ -166,46 +182,44 @@ int lz77_gpu_device_count(void)
     return n;
 }
 
-void lz77_gpu_shutdown(void)
+namespace {
+
+void destroy_context(Context &c)
 {
-    if (!g.ready) return;
-    cudaSetDevice(g.device);
-    cudaStreamSynchronize(g.stream);
-    for (auto &e : g.ev) cudaEventDestroy(e);
-    for (auto &e : g.pool) cudaEventDestroy(e);
-    if (g.scratch) cudaFree(g.scratch);
-    if (g.jump) cudaFree(g.jump);
-    bigwin_release();
-    if (g.stage_in) cudaFree(g.stage_in);
-    if (g.stage_out) cudaFree(g.stage_out);
-    if (g.pinned) cudaFreeHost(g.pinned);
-    if (g.pinned_totals) cudaFreeHost(g.pinned_totals);
-    if (g.copy_in) cudaStreamDestroy(g.copy_in);
-    if (g.copy_out) cudaStreamDestroy(g.copy_out);
-    if (g.aux) cudaStreamDestroy(g.aux);
-    if (g.aux2) cudaStreamDestroy(g.aux2);
-    if (g.hi) cudaStreamDestroy(g.hi);
-    cudaStreamDestroy(g.own_stream);
-    g = Context();
+    if (!c.ready) return;
+    cudaSetDevice(c.device);
+    cudaDeviceSynchronize();
+    comm_release(c);
+    for (auto &e : c.ev) cudaEventDestroy(e);
+    for (auto &e : c.pool) cudaEventDestroy(e);
+    if (c.scratch) cudaFree(c.scratch);
+    if (c.jump) cudaFree(c.jump);
+    bigwin_release(c.device);
+    if (c.stage_in) cudaFree(c.stage_in);
+    if (c.stage_out) cudaFree(c.stage_out);
+    if (c.xfer) cudaFree(c.xfer);
+    if (c.user_in) cudaFree(c.user_in);
+    if (c.user_out) cudaFree(c.user_out);
+    if (c.pinned) cudaFreeHost(c.pinned);
+    if (c.pinned_totals) cudaFreeHost(c.pinned_totals);
+    if (c.copy_in) cudaStreamDestroy(c.copy_in);
+    if (c.copy_out) cudaStreamDestroy(c.copy_out);
+    if (c.aux) cudaStreamDestroy(c.aux);
+    if (c.aux2) cudaStreamDestroy(c.aux2);
+    if (c.hi) cudaStreamDestroy(c.hi);
+    cudaStreamDestroy(c.own_stream);
+    c = Context();
 }
 
-int lz77_gpu_init(int device)
+int create_context(Context &c, int device)
 {
-    if (g.ready && g.device == device) return LZ77_OK;
-    if (g.ready) lz77_gpu_shutdown();
-    int n = lz77_gpu_device_count();
-    if (n <= 0) {
-        snprintf(g.err, sizeof g.err, "no CUDA device visible");
-        return LZ77_E_NODEVICE;
-    }
-    if (device < 0 || device >= n) return LZ77_E_ARG;
     CK(cudaSetDevice(device));
-    CK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
-    g.stream = g.own_stream;
-    for (auto &e : g.ev) CK(cudaEventCreate(&e));
-    CK(cudaMallocHost((void **)&g.pinned, 256));
-    CK(cudaStreamCreateWithFlags(&g.copy_in, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g.copy_out, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    for (auto &e : c.ev) CK(cudaEventCreate(&e));
+    CK(cudaMallocHost((void **)&c.pinned, 256));
+    CK(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
     {
         // The long kernels of the chunked host pipelines (search, tile decode) run on
         // low-priority streams and the short ones that follow each chunk (token-count
@@ -214,16 +228,50 @@ int lz77_gpu_init(int device)
         // with them the D2H copies -- only run after the last search.
         int lo_pri = 0, hi_pri = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-        CK(cudaStreamCreateWithPriority(&g.aux, cudaStreamNonBlocking, lo_pri));
-        CK(cudaStreamCreateWithPriority(&g.aux2, cudaStreamNonBlocking, lo_pri));
-        CK(cudaStreamCreateWithPriority(&g.hi, cudaStreamNonBlocking, hi_pri));
+        CK(cudaStreamCreateWithPriority(&c.aux, cudaStreamNonBlocking, lo_pri));
+        CK(cudaStreamCreateWithPriority(&c.aux2, cudaStreamNonBlocking, lo_pri));
+        CK(cudaStreamCreateWithPriority(&c.hi, cudaStreamNonBlocking, hi_pri));
     }
-    CK(cudaHostAlloc((void **)&g.pinned_totals, kMaxHostChunks * sizeof(unsigned long long),
+    CK(cudaHostAlloc((void **)&c.pinned_totals, kMaxHostChunks * sizeof(unsigned long long),
                      cudaHostAllocMapped));
-    CK(cudaHostGetDevicePointer((void **)&g.pinned_totals_dev, g.pinned_totals, 0));
-    g.device = device;
-    g.ready = true;
-    memset(&g.last, 0, sizeof g.last);
+    CK(cudaHostGetDevicePointer((void **)&c.pinned_totals_dev, c.pinned_totals, 0));
+    c.device = device;
+    memset(&c.last, 0, sizeof c.last);
+    memset(&c.comm_last, 0, sizeof c.comm_last);
+    c.ready = true;
+    return LZ77_OK;
+}
+
+}  // namespace
+
+// Destroys every context of the process.  No other thread may be inside the library.
+void lz77_gpu_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    for (int d = 0; d < kMaxDevices; d++) destroy_context(g_ctx[d]);
+    g_default.store(nullptr, std::memory_order_release);
+    t_ctx = nullptr;
+}
+
+int lz77_gpu_init(int device)
+{
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    int n = lz77_gpu_device_count();
+    if (n <= 0) {
+        snprintf(g.err, sizeof g.err, "no CUDA device visible");
+        return LZ77_E_NODEVICE;
+    }
+    if (device < 0 || device >= n || device >= kMaxDevices) return LZ77_E_ARG;
+    Context &c = g_ctx[device];
+    t_ctx = &c;  // errors of the calls below land in this context
+    if (!c.ready) {
+        int rc = create_context(c, device);
+        if (rc != LZ77_OK) {
+            t_ctx = nullptr;
+            return rc;
+        }
+    }
+    g_default.store(&c, std::memory_order_release);
     return LZ77_OK;
 }
 
@@ -264,7 +312,14 @@ void lz77_gpu_set_timing(int enabled) { g.timing = enabled != 0; }
 void lz77_gpu_set_host_chunk(long bytes)
 {
     // <= 0: no chunking (one H2D, the kernels, one D2H)
-    kHostChunkBytes = bytes > 0 ? bytes : (1ll << 62);
+    g.host_chunk = bytes > 0 ? bytes : (1ll << 62);
+}
+
+int lz77_gpu_set_jump_piece(long bytes)
+{
+    if (bytes != 0 && (bytes < (1L << 20) || bytes > (256L << 20))) return LZ77_E_ARG;
+    g.jump_piece = bytes;
+    return LZ77_OK;
 }
 
 int lz77_gpu_set_stream(void *cuda_stream)
@@ -360,6 +415,7 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         // chunks must not overlap)
         const bool split_search = P.window <= 8191;
         // the copy streams start after whatever the compute stream still has queued
+        StreamDrain drain(g);
         CK(cudaEventRecord(g.ev[4], g.stream));
         CK(cudaStreamWaitEvent(g.copy_in, g.ev[4], 0));
         CK(cudaStreamWaitEvent(g.copy_out, g.ev[4], 0));
@@ -458,19 +514,6 @@ namespace {
 #endif
 constexpr int kJumpWindowMax = LZ77_JUMP_WINDOW_MAX;  // windows up to this decode by pointer jumping
 
-// header parse, lz77.c:157-158; the header always travels through the host
-int read_header(const unsigned char hdr[4], long n_in, Params *P, long long *n_tokens)
-{
-    if (n_in < 4) return LZ77_E_STREAM;
-    const int sb = hdr[0] | (hdr[1] << 8);
-    const int la = hdr[2] | (hdr[3] << 8);
-    if (sb < 1 || la < 1 || la > LZ77_MAX_LA) return LZ77_E_STREAM;  // bitof(0) is undefined
-    if (make_params(sb, la, P) != LZ77_OK) return LZ77_E_STREAM;
-    // lz77.c:271-280: a short read ends the stream, so trailing bits < T are padding
-    *n_tokens = ((long long)(n_in - 4) * 8) / P->tbits;
-    return LZ77_OK;
-}
-
 // runs pass 1; on success *n_out is the decoded size
 int decode_scan_device(const void *d_in, long n_in, Params *P, long long *n_tokens, long *n_out,
                        bool *cross_block)
@@ -549,6 +592,7 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
     if (!evp) return LZ77_E_CUDA;
     cudaEvent_t *ev_in = evp, *ev_scan = evp + n_chunks, *ev_tiles = evp + 2 * n_chunks;
     const size_t in_cap = ((size_t)n_in + 15) & ~(size_t)15;
+    StreamDrain drain(g);
     CK(cudaMemsetAsync((char *)g.stage_in + (in_cap - 16), 0, 32, g.stream));
     CK(cudaEventRecord(g.ev[4], g.stream));
     CK(cudaStreamWaitEvent(g.copy_in, g.ev[4], 0));
@@ -611,7 +655,7 @@ int decode_pipelined(const unsigned char *in, long n_in, unsigned char *out, lon
         if (tile_end > tiles_done) {
             CK(cudaStreamWaitEvent(g.aux, ev_scan[c], 0));
             if (cross) {
-                const long long piece = decode_jump_piece(max_out, P);
+                const long long piece = decode_jump_piece(max_out, P, g.jump_piece);
                 if ((rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes(piece)))) return rc;
                 CK(launch_decode_jump_range((const uint32_t *)g.stage_in, n_in, K,
                                             tiles_done << P.tile_shift,
@@ -718,7 +762,7 @@ int lz77_gpu_decode_device(const void *d_in, long n_in, void *d_out, long out_ca
     if (n == 0) return LZ77_OK;
     if (!d_out || (((uintptr_t)d_out) & 15)) return LZ77_E_ARG;
     if (out_cap < n) return LZ77_E_SPACE;
-    const long long piece = decode_jump_piece(n, P);
+    const long long piece = decode_jump_piece(n, P, g.jump_piece);
     if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes(piece)))) return rc;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
     CK(launch_decode_copy((const uint32_t *)d_in, n_in, k, n, cross, P, g.scratch, g.jump, piece,
@@ -789,7 +833,7 @@ int lz77_gpu_decode(const unsigned char *in, long n_in, unsigned char *out, long
     if (out_cap < n) return LZ77_E_SPACE;
     rc = grow(&g.stage_out, &g.stage_out_cap, (((size_t)n + 15) & ~(size_t)15) + 16);
     if (rc) return rc;
-    const long long piece = decode_jump_piece(n, P);
+    const long long piece = decode_jump_piece(n, P, g.jump_piece);
     if (cross && (rc = grow(&g.jump, &g.jump_cap, decode_jump_scratch_bytes(piece)))) return rc;
     if (g.timing) CK(cudaEventRecord(g.ev[2], g.stream));
     CK(launch_decode_copy((const uint32_t *)g.stage_in, n_in, k, n, cross, P, g.scratch, g.jump,

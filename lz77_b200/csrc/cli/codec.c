@@ -21,9 +21,13 @@ struct bitFILE {
     int mode;
 };
 
-static int g_device = 0;
+static int g_device = 0, g_gpus = 1;
+static long g_piece_mib = 1024, g_out_mib = 4096;
 
 void lz77_cli_set_device(int device) { g_device = device; }
+void lz77_cli_set_gpus(int n) { g_gpus = n < 1 ? 1 : n; }
+void lz77_cli_set_piece_mib(long mib) { g_piece_mib = mib < 1 ? 1 : mib; }
+void lz77_cli_set_out_mib(long mib) { g_out_mib = mib < 1 ? 1 : mib; }
 
 struct bitFILE *bitIO_open(const char *path, int mode)
 {
@@ -63,23 +67,33 @@ static void die(const char *what, int rc)
 
 static void bind_device(void)
 {
-    int rc = lz77_gpu_init(g_device);
+    int rc = g_gpus > 1 ? lz77_mgpu_init(g_gpus) : lz77_gpu_init(g_device);
     if (rc != LZ77_OK)
         die("initialising the GPU", rc);
+}
+
+/* one library call: the bound device, or every device of -G */
+static int codec_encode(const unsigned char *in, long n_in, int sb, int la, unsigned char *out,
+                        long cap, long *n_out)
+{
+    if (g_gpus > 1)
+        return lz77_mgpu_encode(in, n_in, sb, la, out, cap, n_out);
+    return lz77_gpu_encode(in, n_in, sb, la, out, cap, n_out);
+}
+
+static int codec_decode(const unsigned char *in, long n_in, unsigned char *out, long cap,
+                        long *n_out)
+{
+    if (g_gpus > 1)
+        return lz77_mgpu_decode(in, n_in, out, cap, n_out);
+    return lz77_gpu_decode(in, n_in, out, cap, n_out);
 }
 
 /* Bytes of input encoded per library call.  The encoder's blocks are independent,
  * so the stream of a large file is the streams of its pieces back to back: the
  * file never has to fit in (pinned) memory, like the reference's O(1)-memory
  * window loop (lz77.c:78,113-129).  A multiple of every block size. */
-static long piece_bytes(void)
-{
-    const char *e = getenv("LZ77_CLI_PIECE_MIB"); /* test hook */
-    long mib = e ? atol(e) : 1024;
-    if (mib < 1)
-        mib = 1;
-    return mib << 20;
-}
+static long piece_bytes(void) { return g_piece_mib << 20; }
 
 /* appends `nbits` bits (LSB-first, bitio.c:203-239) of src to the output file;
  * *acc / *acc_bits carry the bits of the last, still incomplete byte */
@@ -151,7 +165,7 @@ void encode(FILE *file, struct bitFILE *out, int la, int sb)
             if (obuf == NULL)
                 die("allocating the output buffer", LZ77_E_NOMEM);
         }
-        rc = lz77_gpu_encode(in, n_in, sb, la, obuf, cap, &n_out);
+        rc = codec_encode(in, n_in, sb, la, obuf, cap, &n_out);
         if (rc != LZ77_OK)
             die("encoding", rc);
         if (first && fwrite(obuf, 1, 4, out->file) != 4) /* header, lz77.c:74-75 */
@@ -199,13 +213,6 @@ static void copy_bits(unsigned char *dst, long dst_bit, const unsigned char *src
     }
 }
 
-static long env_mib(const char *name, long dflt)
-{
-    const char *e = getenv(name);
-    long mib = e ? atol(e) : dflt;
-    return (mib < 1 ? 1 : mib) << 20;
-}
-
 /*
  * The stream is decoded in pieces of tokens, so neither the compressed file nor
  * the output has to fit in memory (the reference's loop keeps SB bytes,
@@ -222,7 +229,7 @@ void decode(struct bitFILE *file, FILE *out)
     unsigned char hdr[4];
     unsigned char *raw, *sbuf = NULL, *obuf = NULL, *hist;
     long sbuf_cap = 0, obuf_cap = 0, hist_len = 0, raw_cap, piece_tokens;
-    long out_limit = env_mib("LZ77_CLI_OUT_MIB", 4096);
+    long out_limit = g_out_mib << 20;
     int sb, la, ob, lb, tbits, rc, last = 0;
     long block;
 
@@ -301,7 +308,7 @@ void decode(struct bitFILE *file, FILE *out)
                 if (obuf == NULL)
                     die("allocating the output buffer", LZ77_E_NOMEM);
             }
-            rc = lz77_gpu_decode(sbuf, (bit + 7) / 8, obuf, obuf_cap, &m);
+            rc = codec_decode(sbuf, (bit + 7) / 8, obuf, obuf_cap, &m);
             if (rc != LZ77_OK)
                 die("decoding", rc);
             if (m > hist_len &&

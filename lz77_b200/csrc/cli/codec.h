@@ -20,7 +20,13 @@ int bitIO_close(struct bitFILE *bitF);                  /* bitio.c:171 */
 void encode(FILE *file, struct bitFILE *out, int la, int sb); /* lz77.c:51  */
 void decode(struct bitFILE *file, FILE *out);                 /* lz77.c:148 */
 
-/* additive knob: CUDA device the codec binds to (default 0) */
+/* additive knobs: CUDA device the codec binds to (default 0); number of GPUs (default 1:
+ * > 1 shards every piece over the first n devices, lz77_mgpu_*); input bytes per library
+ * call (encode: default 1 GiB; decode: a quarter of it in stream bytes) and decoded bytes
+ * per library call (default 4 GiB) -- files of any size stream through in pieces */
 void lz77_cli_set_device(int device);
+void lz77_cli_set_gpus(int n);
+void lz77_cli_set_piece_mib(long mib);
+void lz77_cli_set_out_mib(long mib);
 
 #endif

@@ -1,7 +1,10 @@
 /*
  * lz77_cli.c -- command-line driver with the reference's surface (main.c:59-181):
  *   lz77 -c|-d -i <in> -o <out> [-l 2..255] [-s 0..65535] [-h]
- * Same getopt string plus one additive option, -g <device>.  Same limits
+ * Same getopt string plus additive options that leave the file format alone: -g <device>,
+ * -G <n> (encode / decode on the first n GPUs: runs of whole blocks per GPU, NCCL
+ * scatter / gather inside liblz77b200.so), -p <MiB> (input bytes per library call) and
+ * -m <MiB> (decoded bytes per library call).  Same limits
  * (main.c:35-38), same messages and exit codes: every usage or open error
  * prints the reference's text on stderr and exits EXIT_FAILURE; -h prints the
  * usage and continues; the last of -c / -d wins; -d ignores -l / -s (the
@@ -38,7 +41,7 @@ int main(int argc, char *argv[])
     struct bitFILE *packed = NULL;
     int opt;
 
-    while ((opt = getopt(argc, argv, "cdi:o:l:s:hg:")) != -1) {
+    while ((opt = getopt(argc, argv, "cdi:o:l:s:hg:G:p:m:")) != -1) {
         switch (opt) {
         case 'c':
             mode = MODE_ENCODE;
@@ -79,6 +82,15 @@ int main(int argc, char *argv[])
             break;
         case 'g':
             lz77_cli_set_device(atoi(optarg));
+            break;
+        case 'G':
+            lz77_cli_set_gpus(atoi(optarg));
+            break;
+        case 'p':
+            lz77_cli_set_piece_mib(atol(optarg));
+            break;
+        case 'm':
+            lz77_cli_set_out_mib(atol(optarg));
             break;
         default:
             break;

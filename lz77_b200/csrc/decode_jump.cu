@@ -30,8 +30,6 @@
 // pointer width.  Measured on B200: larger pieces and more hops per pass are faster
 // (fewer launches; S does not stay L2-resident even at 16 MiB pieces): 16 / 32 / 64 MiB
 // pieces decode text at 60 / 67 / 75 GB/s.
-#include <cstdlib>
-
 #include "kernels.cuh"
 
 namespace lz77 {
@@ -54,14 +52,10 @@ constexpr int kMaxJumpPasses = 40;
 
 // Output bytes per piece for a stream that decodes to at most n_out_max bytes: the
 // full piece, or the whole (tile-rounded) output when that is smaller.
-long long decode_jump_piece(long long n_out_max, const Params &P)
+long long decode_jump_piece(long long n_out_max, const Params &P, long long override_bytes)
 {
     const long long tile = 1LL << P.tile_shift;
-    long long cap = kJumpPiece;
-    if (const char *e = getenv("LZ77_JUMP_PIECE_MIB")) {  // test hook: several pieces on small streams
-        const long long mib = atoll(e);
-        if (mib >= 1 && mib <= 256) cap = mib << 20;
-    }
+    const long long cap = override_bytes > 0 ? override_bytes : kJumpPiece;  // lz77_gpu_set_jump_piece()
     const long long whole = (n_out_max + tile - 1) / tile * tile;
     return whole < cap ? (whole > tile ? whole : tile) : cap;
 }

@@ -2,8 +2,8 @@
 //
 // Replaces, for a batch of independent blocks at once:
 //   tree.c:62-260 (BST insert/find/delete/updateOffset)  -> shared-memory
-//       windowed warp search: bucketed in search_bucket.cu / search_bigwin.cu
-//       (the default), exhaustive in lz77_parse_kernel below (cross-check)
+//       windowed warp search over position buckets: search_bucket.cu (windows
+//       <= 8191) and search_bigwin.cu (larger windows)
 //   lz77.c:89-135 (greedy token loop, match() lz77.c:209-224) -> one warp per
 //       parse segment, sequential in the segment, parallel across segments
 //   lz77.c:246-252 writecode + bitio.c:203-239 bitIO_write -> warp-cooperative
@@ -15,148 +15,12 @@
 // offset among the longest (keeps the decoder's dependency chains short), then
 // a literal.
 #include "kernels.cuh"
-#include "match.cuh"
 
 namespace lz77 {
 
 // ---------------------------------------------------------------------------
-// K1 (first generation, kept as a cross-check: -DLZ77_EXHAUSTIVE_SCAN=1 routes
-// large windows here): exhaustive longest-match search + greedy parse
-// ---------------------------------------------------------------------------
-//
-// One CTA stages `hist` history bytes + nwarps*kSegBytes input bytes into
-// shared memory with one TMA bulk copy; warp w then parses segment w.  For every
-// token the warp scans the window oldest-first in 512-byte chunks: each lane
-// takes one 16-byte group (LDS.128), filters the 16 candidate starts on the
-// first target byte with an exact SWAR zero-byte test, verifies survivors
-// against the target held in registers, and the (length, oldest start) pair is
-// reduced warp-wide with REDUX.  A chunk that yields a maximum-length match
-// ends the scan early.
-
-template <bool kSmallLA>
-__global__ void __launch_bounds__(1024, 1)
-lz77_parse_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
-                  uint32_t *__restrict__ tok_tmp, uint32_t *__restrict__ seg_ntok)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mbar;
-
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int nwarps = blockDim.x >> 5;
-    const long long tile_bytes = (long long)nwarps * kSegBytes;
-    const long long tile_lo = (long long)blockIdx.x * tile_bytes;
-    const long long blk_lo = (tile_lo >> P.block_shift) << P.block_shift;
-
-    // ---- stage history + tile -------------------------------------------
-    long long hist = tile_lo - blk_lo;
-    if (hist > P.window) hist = P.window;
-    const int hist_al = (int)((hist + 15) & ~15LL);  // <= tile_lo - blk_lo (both multiples of 16)
-    const long long src_lo = tile_lo - hist_al;
-    long long src_hi = tile_lo + tile_bytes;
-    if (src_hi > n) src_hi = n;
-    const int bytes = (int)(src_hi - src_lo);
-    const int bulk = bytes & ~15;
-    const int dst0 = hist_cap - hist_al;  // smem index of global byte src_lo
-
-    if (threadIdx.x == 0) {
-        mbar_init(&mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && bulk > 0) {
-        mbar_expect_tx(&mbar, (uint32_t)bulk);
-        tma_load_1d(smem + dst0, in + src_lo, (uint32_t)bulk, &mbar);
-    }
-    // ragged tail (< 16 bytes) and zero padding behind the data
-    for (int i = bulk + threadIdx.x; i < bytes + 64; i += blockDim.x)
-        smem[dst0 + i] = (i < bytes) ? in[src_lo + i] : (uint8_t)0;
-    if (bulk > 0) mbar_wait(&mbar, 0);
-    __syncthreads();
-
-    // ---- parse this warp's segment ---------------------------------------
-    const long long seg_lo = tile_lo + (long long)warp * kSegBytes;
-    const long long sgm = (long long)blockIdx.x * nwarps + warp;  // global segment index
-    if (seg_lo >= n) return;
-    long long seg_hi = seg_lo + kSegBytes;
-    if (seg_hi > n) seg_hi = n;
-
-    const int seg_end = (int)(seg_hi - src_lo) + dst0;  // smem index one past the segment
-    int p0 = (int)(seg_lo - src_lo) + dst0;             // smem index of the parse position
-    const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // smem index of the block start (may be < 0)
-    uint32_t *tok_out = tok_tmp + sgm * kSegBytes;
-    const int len_shift = P.ob, lit_shift = P.ob + P.lb;
-
-    int ntok = 0;
-    uint32_t held = 0;  // lane l holds token (ntok & ~31) + l until the row is flushed
-
-    while (p0 < seg_end) {
-        const int max_len = min(P.la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
-        const int reach = min(p0 - blk_idx, P.window);    // lz77.c:101-105
-        uint32_t key = 0;                                 // best (len << 20 | start index)
-
-        if (max_len > 0 && reach > 0) {
-            const int lo_idx = p0 - reach;
-            uint32_t tgt[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) tgt[i] = lds_u32_unaligned(smem, p0 + 4 * i);
-            const uint32_t b0x4 = (uint32_t)smem[p0] * 0x01010101u;
-            int best_len = 0, best_q = 0;
-
-            for (int base = lo_idx & ~15; base < p0; base += 512) {  // oldest chunk first
-                const int g = base + lane * 16;
-                if (g < p0) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(smem + g);
-                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        uint32_t m = zero_bytes(wv[i] ^ b0x4);
-                        while (m) {
-                            const int bit = __ffs(m) - 1;
-                            m ^= 1u << bit;
-                            const int q = g + 4 * i + (bit >> 3);
-                            if (q >= lo_idx && q < p0) {
-                                // nearer than anything this lane has seen: must be longer
-                                const int l = match_len<kSmallLA>(smem, q, p0, tgt, max_len);
-                                if (l > best_len) {
-                                    best_len = l;
-                                    best_q = q;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (__any_sync(0xffffffffu, best_len >= max_len)) break;
-            }
-            // longest first, then the oldest start
-            key = __reduce_max_sync(0xffffffffu,
-                                    best_len ? ((uint32_t)best_len << 20) |
-                                                   (0xfffffu - (uint32_t)best_q) : 0u);
-        }
-
-        const int len = (int)(key >> 20);
-        const int off = len ? p0 - (int)(0xfffffu - (key & 0xfffffu)) : 0;
-        const uint32_t lit = smem[p0 + len];
-        const uint32_t tok = (uint32_t)off | ((uint32_t)len << len_shift) | (lit << lit_shift);
-
-        if (lane == (ntok & 31)) held = tok;
-        ntok++;
-        if ((ntok & 31) == 0) tok_out[ntok - 32 + lane] = held;  // coalesced 128 B row
-        p0 += len + 1;
-    }
-    if (lane < (ntok & 31)) tok_out[(ntok & ~31) + lane] = held;
-    if (lane == 0) seg_ntok[sgm] = (uint32_t)ntok;
-}
-
-// ---------------------------------------------------------------------------
 // token-count prefix sums (uint32 counts -> uint64 exclusive prefix)
 // ---------------------------------------------------------------------------
-
-#ifndef LZ77_EXHAUSTIVE_SCAN
-#define LZ77_EXHAUSTIVE_SCAN 0
-#endif
-// 1: large windows use the exhaustive scan above instead of search_bigwin.cu (debugging aid)
-constexpr bool kUseExhaustiveScan = LZ77_EXHAUSTIVE_SCAN != 0;
 
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -379,14 +243,6 @@ static inline char *carve(char *&p, size_t bytes)
     return r;
 }
 
-int encode_parse_config(const Params &P, int *nwarps, int *hist_cap, size_t *smem)
-{
-    *hist_cap = (P.window + 15) & ~15;
-    *nwarps = P.window <= 8191 ? 8 : 32;
-    *smem = (size_t)*hist_cap + (size_t)*nwarps * kSegBytes + 128;
-    return 0;
-}
-
 EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P)
 {
     const long long n_seg = (n_in_total + kSegBytes - 1) / kSegBytes;
@@ -427,32 +283,18 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
     unsigned long long *partial = pl.partial + seg0 / kScanTile;
     unsigned long long *total = pl.total;
 
-    int nwarps, hist_cap;
-    size_t smem;
-    encode_parse_config(P, &nwarps, &hist_cap, &smem);
-    const long long tile_bytes = (long long)nwarps * kSegBytes;
-    const long long n_tiles = (n_chunk + tile_bytes - 1) / tile_bytes;
-    const bool small_la = P.la <= 16;
-
     if (first && phase != 1) cudaMemsetAsync(total, 0, 8, st);
     if (ev) cudaEventRecord(ev->e[0], st);
     if (phase == 2) {
         // searched by an earlier phase-1 call
-    } else if (n_tiles > 0 && P.window <= 8191) {
+    } else if (n_chunk > 0 && P.window <= 8191) {
         // small windows: bucketed search (search_bucket.cu)
         cudaError_t rc = launch_parse_bucket(d_in, n_chunk, P, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
-    } else if (n_tiles > 0 && !kUseExhaustiveScan) {
+    } else if (n_chunk > 0) {
         // large windows: block-level buckets (search_bigwin.cu)
         cudaError_t rc = launch_parse_bigwin(d_in, n_chunk, P, pl.big, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
-    } else if (n_tiles > 0) {
-        auto kern = small_la ? lz77_parse_kernel<true> : lz77_parse_kernel<false>;
-        cudaError_t rc =
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (rc != cudaSuccess) return rc;
-        kern<<<(unsigned)n_tiles, nwarps * 32, smem, st>>>(d_in, n_chunk, P, hist_cap, tok_tmp,
-                                                            seg_ntok);
     }
     if (ev) cudaEventRecord(ev->e[1], st);
     if (phase == 1) return cudaGetLastError();

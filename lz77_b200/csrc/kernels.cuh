@@ -44,7 +44,7 @@ cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Param
                                 void *scratch, uint32_t *tok_tmp, uint32_t *seg_ntok,
                                 cudaStream_t st);
 
-void bigwin_release();  // side stream + events of the large-window encoder
+void bigwin_release(int device);  // side stream + events of the large-window encoder
 
 // ---- decoder (decode.cu) ---------------------------------------------------
 struct DecodeInfo {            // lives in device scratch, copied back by the C ABI
@@ -94,7 +94,8 @@ cudaError_t launch_decode_copy(const uint32_t *d_in_words, long long n_in_bytes,
                                long long n_tokens, long long n_out, bool cross_block,
                                const Params &P, void *scratch, void *jump_scratch,
                                long long jump_piece, uint8_t *d_out, cudaStream_t st);
-long long decode_jump_piece(long long n_out_max, const Params &P);  // output bytes per round
+// output bytes per round (override: bytes per piece, 0 = the default)
+long long decode_jump_piece(long long n_out_max, const Params &P, long long override_bytes);
 size_t decode_jump_scratch_bytes(long long jump_piece);
 cudaError_t launch_decode_jump_range(const uint32_t *d_in_words, long long n_in_bytes,
                                      long long n_tokens, long long out_lo, long long out_hi,

@@ -362,44 +362,48 @@ size_t bigwin_scratch_bytes(long long n_in, const Params &P)
 
 namespace {
 struct BigwinStreams {
-    int device = -1;
+    bool ready = false;
     cudaStream_t sort = nullptr;   // high priority: its few CTAs slip in between parse CTAs
     cudaEvent_t fork = nullptr, sorted[2] = {nullptr, nullptr}, parsed[2] = {nullptr, nullptr};
 };
-BigwinStreams g_bw;
+BigwinStreams g_bw_dev[16];  // per device (one host thread drives one device)
 
-cudaError_t bigwin_streams()
+cudaError_t bigwin_streams(BigwinStreams **out)
 {
     int dev = 0;
     cudaError_t rc = cudaGetDevice(&dev);
     if (rc != cudaSuccess) return rc;
-    if (g_bw.device == dev) return cudaSuccess;
+    if (dev < 0 || dev >= 16) return cudaErrorInvalidDevice;
+    BigwinStreams &bw = g_bw_dev[dev];
+    *out = &bw;
+    if (bw.ready) return cudaSuccess;
     int lo_pri = 0, hi_pri = 0;
     rc = cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
     if (rc != cudaSuccess) return rc;
-    rc = cudaStreamCreateWithPriority(&g_bw.sort, cudaStreamNonBlocking, hi_pri);
+    rc = cudaStreamCreateWithPriority(&bw.sort, cudaStreamNonBlocking, hi_pri);
     if (rc != cudaSuccess) return rc;
-    cudaEventCreateWithFlags(&g_bw.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&bw.fork, cudaEventDisableTiming);
     for (int i = 0; i < 2; i++) {
-        cudaEventCreateWithFlags(&g_bw.sorted[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&g_bw.parsed[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&bw.sorted[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&bw.parsed[i], cudaEventDisableTiming);
     }
-    g_bw.device = dev;
+    bw.ready = true;
     return cudaGetLastError();
 }
 }  // namespace
 
-// called by lz77_gpu_shutdown()
-void bigwin_release()
+// called by lz77_gpu_shutdown() with the device current
+void bigwin_release(int device)
 {
-    if (g_bw.device < 0) return;
-    cudaStreamDestroy(g_bw.sort);
-    cudaEventDestroy(g_bw.fork);
+    if (device < 0 || device >= 16 || !g_bw_dev[device].ready) return;
+    BigwinStreams &bw = g_bw_dev[device];
+    cudaStreamDestroy(bw.sort);
+    cudaEventDestroy(bw.fork);
     for (int i = 0; i < 2; i++) {
-        cudaEventDestroy(g_bw.sorted[i]);
-        cudaEventDestroy(g_bw.parsed[i]);
+        cudaEventDestroy(bw.sorted[i]);
+        cudaEventDestroy(bw.parsed[i]);
     }
-    g_bw = BigwinStreams();
+    bw = BigwinStreams();
 }
 
 // d_in points at a block boundary.  The input is handled in pieces of kBigPiece
@@ -410,8 +414,10 @@ cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Param
                                 cudaStream_t st)
 {
     if (n_in <= 0) return cudaSuccess;
-    cudaError_t rc = bigwin_streams();
+    BigwinStreams *bwp = nullptr;
+    cudaError_t rc = bigwin_streams(&bwp);
     if (rc != cudaSuccess) return rc;
+    BigwinStreams &g_bw = *bwp;
     const size_t piece_scratch = bigwin_piece_scratch(n_in < kBigPiece ? n_in : kBigPiece, P);
     const size_t sort_smem = (size_t)kSortWarps * (1 << kBigB0Bits) * 4 + (size_t)kBigBuckets * 4;
     rc = cudaFuncSetAttribute(lz77_block_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

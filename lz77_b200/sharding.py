@@ -208,7 +208,10 @@ def decode_sharded(stream: torch.Tensor | None, block: int, token_bits: int, cod
          and the outputs travel to root with point-to-point sends.
     Root returns the decoded bytes (uint8 tensor on `device`), the other ranks None.
     Streams of the reference encoder are not block-structured (a match may reach
-    back SB bytes from anywhere): replicas only, ValueError here."""
+    back SB bytes from anywhere): replicas only, ValueError here -- on EVERY rank, after
+    the collective in which the ranks compare notes (a rank that raised on its own would
+    leave the others waiting in the next all-gather).  The same holds for a codec error
+    on one rank: it travels as a flag and every rank raises."""
     dist = _dist()
     rank, world = dist.get_rank(), dist.get_world_size()
     meta = torch.zeros(2, dtype=torch.int64, device=device)
@@ -241,29 +244,45 @@ def decode_sharded(stream: torch.Tensor | None, block: int, token_bits: int, cod
         local = torch.empty(nbytes[rank], dtype=torch.uint8, device=device)
         dist.recv(local, src=root)
     k_lo, k_hi = slices[rank]
+
+    def gather_i64(value: int) -> List[int]:
+        got = torch.zeros(world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(got, torch.tensor([value], dtype=torch.int64, device=device))
+        return [int(v) for v in got.cpu().tolist()]
+
     # 2. decoded size of the own tokens -> decoded position of every slice
-    own = codec.decode_size(codec.slice_tokens(local, 0, k_hi - k_lo))
-    sums = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(sums, torch.tensor([own], dtype=torch.int64, device=device))
-    sums = [int(v) for v in sums.cpu().tolist()]
+    #    (-1 = this rank's codec failed; every rank sees it in the same all-gather)
+    try:
+        own = codec.decode_size(codec.slice_tokens(local, 0, k_hi - k_lo))
+    except Exception:  # noqa: BLE001 -- reported collectively below
+        own = -1
+    sums = gather_i64(own)
+    if min(sums) < 0:
+        raise ValueError(f"rank {sums.index(min(sums))} could not read its token slice")
     pos = sum(sums[:rank])
-    # 3. first block boundary at or after the slice start -> split token
+    # 3. first block boundary at or after the slice start -> split token (-1 = no token
+    #    starts there: not a stream of the block encoder)
     to_boundary = (-pos) % block
-    k_rel, k_pos = codec.token_at(local, to_boundary)
-    if k_pos != to_boundary:
+    try:
+        k_rel, k_pos = codec.token_at(local, to_boundary)
+        split = k_lo + k_rel if k_pos == to_boundary else -1
+    except Exception:  # noqa: BLE001
+        split = -1
+    splits = gather_i64(split)
+    if min(splits) < 0:
         raise ValueError("no token starts on the block boundary: not a stream of the block encoder")
-    splits = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(splits, torch.tensor([k_lo + k_rel], dtype=torch.int64,
-                                                     device=device))
-    splits = [int(v) for v in splits.cpu().tolist()] + [n_tokens]
+    splits = splits + [n_tokens]
     a, b = splits[rank] - k_lo, splits[rank + 1] - k_lo
     # 4. decode the run of whole blocks, gather at root
-    part = codec.decode(codec.slice_tokens(local, a, b)) if b > a else \
-        torch.empty(0, dtype=torch.uint8, device=device)
-    sizes = torch.zeros(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(sizes, torch.tensor([part.numel()], dtype=torch.int64,
-                                                    device=device))
-    sizes = [int(v) for v in sizes.cpu().tolist()]
+    try:
+        part = codec.decode(codec.slice_tokens(local, a, b)) if b > a else \
+            torch.empty(0, dtype=torch.uint8, device=device)
+        size = part.numel()
+    except Exception:  # noqa: BLE001
+        part, size = None, -1
+    sizes = gather_i64(size)
+    if min(sizes) < 0:
+        raise ValueError(f"rank {sizes.index(min(sizes))} could not decode its blocks")
     if rank != root:
         if sizes[rank] > 0:
             dist.send(part.contiguous(), dst=root)

@@ -349,15 +349,14 @@ def test_cli_streams_large_files_in_pieces(lz, orc, tmp_path, args):
     fin.write_bytes(data)
     one, pieces, back = tmp_path / "one.lz", tmp_path / "pieces.lz", tmp_path / "back.bin"
     subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(one), *args], check=True)
-    env = dict(os.environ, LZ77_CLI_PIECE_MIB="1")
-    subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(pieces), *args], check=True, env=env)
+    subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(pieces), "-p", "1", *args], check=True)
     assert pieces.read_bytes() == one.read_bytes()
     subprocess.run([str(cli), "-d", "-i", str(pieces), "-o", str(back)], check=True)
     assert back.read_bytes() == data
     # empty input: header only
     empty = tmp_path / "empty.bin"
     empty.write_bytes(b"")
-    subprocess.run([str(cli), "-c", "-i", str(empty), "-o", str(one), *args], check=True, env=env)
+    subprocess.run([str(cli), "-c", "-i", str(empty), "-o", str(one), "-p", "1", *args], check=True)
     assert len(one.read_bytes()) == 4
 
 
@@ -374,8 +373,8 @@ def test_cli_decodes_large_files_in_pieces(lz, orc, tmp_path, args):
     fin, own, back = tmp_path / "in.bin", tmp_path / "own.lz", tmp_path / "back.bin"
     fin.write_bytes(data)
     subprocess.run([str(cli), "-c", "-i", str(fin), "-o", str(own), *args], check=True)
-    env = dict(os.environ, LZ77_CLI_PIECE_MIB="1", LZ77_CLI_OUT_MIB="1")
-    subprocess.run([str(cli), "-d", "-i", str(own), "-o", str(back)], check=True, env=env)
+    small_pieces = ["-p", "1", "-m", "1"]
+    subprocess.run([str(cli), "-d", "-i", str(own), "-o", str(back), *small_pieces], check=True)
     assert back.read_bytes() == data
     # a stream of the reference encoder (restated): matches cross every piece seam
     sb = int(args[1]) if args else 4095
@@ -383,13 +382,12 @@ def test_cli_decodes_large_files_in_pieces(lz, orc, tmp_path, args):
     small = text[:1_200_000] + bytes(70_000) + text[1_200_000:1_500_000]
     ref = tmp_path / "ref.lz"
     ref.write_bytes(orc.ref_encode(small, sb, la))
-    env = dict(os.environ, LZ77_CLI_PIECE_MIB="1", LZ77_CLI_OUT_MIB="1")
-    subprocess.run([str(cli), "-d", "-i", str(ref), "-o", str(back)], check=True, env=env)
+    subprocess.run([str(cli), "-d", "-i", str(ref), "-o", str(back), *small_pieces], check=True)
     assert back.read_bytes() == small
     # header only / short header
     for blob in (ref.read_bytes()[:4], b"\xff\x0f"):
         ref.write_bytes(blob)
-        subprocess.run([str(cli), "-d", "-i", str(ref), "-o", str(back)], check=True, env=env)
+        subprocess.run([str(cli), "-d", "-i", str(ref), "-o", str(back), *small_pieces], check=True)
         assert back.read_bytes() == b""
 
 
@@ -492,11 +490,12 @@ def test_decode_unblocked_synthetic_tokens(lz, orc, sb, la, k):
     want = orc.decode(stream)
     assert lz.decode_size(stream) == len(want)
     assert lz.decode(stream) == want
-    os.environ["LZ77_JUMP_PIECE_MIB"] = "8"  # the same in pieces of 8 MiB of output
+    from lz77_b200 import api
+    api.set_jump_piece(8 << 20)  # the same in pieces of 8 MiB of output
     try:
         assert lz.decode(stream) == want
     finally:
-        del os.environ["LZ77_JUMP_PIECE_MIB"]
+        api.set_jump_piece(0)
 
 
 @pytest.mark.parametrize("sb,la", [(4095, 15), (65535, 255)])
@@ -518,11 +517,12 @@ def test_decode_unblocked_deep_chains(lz, orc, sb, la):
     want = orc.decode(stream)
     assert len(want) > (36 << 20)
     assert lz.decode(stream) == want
-    os.environ["LZ77_JUMP_PIECE_MIB"] = "16"  # chains that run through three pieces
+    from lz77_b200 import api
+    api.set_jump_piece(16 << 20)  # chains that run through three pieces
     try:
         assert lz.decode(stream) == want
     finally:
-        del os.environ["LZ77_JUMP_PIECE_MIB"]
+        api.set_jump_piece(0)
 
 
 def test_decode_unblocked_after_blocked_prefix_pipelined(lz, orc):

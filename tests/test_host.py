@@ -223,11 +223,24 @@ def _gloo_decode_worker(rank, world, port, sb, la, n, q):
         decode_size=lambda s: int((parse_tokens(t2b(s))[1] + 1).sum()),
         token_at=token_at,
         decode=lambda s: b2t(orc.decode(t2b(s))))
-    data = synth.zipf_text(n, seed=8).numpy()
+    data = synth.zipf_text(abs(n), seed=8).numpy()
     stream = None
     if rank == 0:
-        whole, _ = orc.blocked_encode(data, sb, la, block, seg)
+        if n < 0:  # what the reference encoder writes: no token on the block boundaries
+            whole = orc.ref_encode(data, sb, la)
+        else:
+            whole, _ = orc.blocked_encode(data, sb, la, block, seg)
         stream = b2t(whole)
+    if n < 0:
+        # every rank must raise (none may be left waiting in a collective)
+        try:
+            sharding.decode_sharded(stream, block, T, codec, "cpu")
+            q.put((rank, "no error"))
+        except ValueError as e:
+            q.put((rank, str(e)))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     out = sharding.decode_sharded(stream, block, T, codec, "cpu")
     if rank == 0:
         k = ((stream.numel() - 4) * 8) // T
@@ -256,6 +269,37 @@ def test_sharded_decode_world2_gloo(sb, la, n, split):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok and was_split == split
+
+
+def test_sharded_decode_reference_stream_fails_on_every_rank_gloo():
+    """A stream of the reference encoder cannot shard: both ranks raise ValueError after
+    the all-gather of the split points; neither is left waiting in a collective."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_decode_worker, args=(r, 2, port, 4095, 15, -700_001, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert set(got) == {0, 1}
+    assert all("not a stream of the block encoder" in msg for msg in got.values()), got
+
+
+def test_shard_range_matches_the_python_bookkeeping():
+    """lz77_shard_range (what the library's NCCL path uses) == sharding.shard_ranges."""
+    from lz77_b200 import api
+    from lz77_b200.sharding import shard_ranges
+    for n, world, block in [(0, 2, 65536), (1, 3, 65536), (5 * 65536 + 17, 2, 65536),
+                            (37 * 65536 + 4321, 4, 65536), (24 * 524288 + 4321, 8, 524288),
+                            (65536, 8, 65536), (1 << 32, 4, 65536)]:
+        want = shard_ranges(n, world, block)
+        got = [api.shard_range(n, world, block, r) for r in range(world)]
+        assert got == want, (n, world, block)
 
 
 @pytest.mark.parametrize("sb,la", [(4095, 15), (1000, 20)])
