@@ -96,6 +96,16 @@ int  lz77_gpu_set_stream(void *cuda_stream);
  * bytes <= 0 turns chunking off. */
 void lz77_gpu_set_host_chunk(long bytes);
 
+/* History mode of the encoder (default off).  Off: independent blocks -- no match
+ * reaches across a multiple of lz77_gpu_block_size(), which is what lets the blocks of
+ * one stream be decoded side by side and one stream be decoded by several GPUs.  On: the
+ * match window slides across block seams exactly like the reference's (the last SB
+ * bytes, wherever they are: lz77.c:101-105, tree.c:118-152), which recovers the
+ * reference's compression ratio at large windows; such streams decode by pointer
+ * jumping (like streams of the reference encoder) and cannot shard for decode.  Either
+ * way the stream is the reference's format and decodes with the reference decoder. */
+void lz77_gpu_set_history(int enabled);
+
 /* Streams the reference encoder wrote (matches that leave their block) are
  * decoded by pointer jumping over pieces of this many output bytes (default
  * 64 MiB, 1 MiB .. 256 MiB; the scratch is 12 bytes per byte of a piece).

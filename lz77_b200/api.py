@@ -30,6 +30,7 @@ EXPORTS = (
     "lz77_gpu_decode_size_device", "lz77_gpu_decode_device", "lz77_gpu_last_timing",
     "lz77_gpu_set_timing", "lz77_gpu_set_stream", "lz77_gpu_set_host_chunk",
     "lz77_gpu_slice_tokens_device", "lz77_gpu_token_at_device", "lz77_gpu_set_jump_piece",
+    "lz77_gpu_set_history",
     "lz77_shard_range", "lz77_comm_get_unique_id", "lz77_comm_init", "lz77_comm_destroy",
     "lz77_gpu_encode_sharded_device", "lz77_gpu_decode_sharded_device", "lz77_comm_last_stats",
     "lz77_mgpu_init", "lz77_mgpu_shutdown", "lz77_mgpu_encode", "lz77_mgpu_decode",
@@ -107,6 +108,7 @@ def load_library() -> C.CDLL:
         "lz77_gpu_slice_tokens_device": (ip, [vp, lp, lp, lp, vp, lp, plong]),
         "lz77_gpu_token_at_device": (ip, [vp, lp, lp, plong, plong]),
         "lz77_gpu_set_jump_piece": (ip, [lp]),
+        "lz77_gpu_set_history": (None, [ip]),
         "lz77_shard_range": (ip, [lp, ip, lp, ip, plong, plong]),
         "lz77_comm_get_unique_id": (ip, [vp]),
         "lz77_comm_init": (ip, [vp, ip, ip]),
@@ -204,6 +206,13 @@ def set_host_chunk(nbytes: int) -> None:
 
 def set_timing(enabled: bool) -> None:
     load_library().lz77_gpu_set_timing(1 if enabled else 0)
+
+
+def set_history(enabled: bool) -> None:
+    """Encoder: let the match window slide across block seams like the reference's
+    (lz77.c:101-105).  Better ratio at large windows; the stream no longer decodes block
+    by block (pointer jumping) and cannot shard for decode."""
+    load_library().lz77_gpu_set_history(1 if enabled else 0)
 
 
 def set_jump_piece(nbytes: int) -> None:

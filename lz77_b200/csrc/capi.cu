@@ -79,6 +79,7 @@ int make_params(int sb, int la, Params *P)
     P->block = lz77_gpu_block_size(sb);
     P->block_shift = bitof((int)P->block);
     P->tile_shift = P->block_shift < 17 ? P->block_shift : 17;
+    P->history = ctx().history ? 1 : 0;
     return LZ77_OK;
 }
 
@@ -315,6 +316,8 @@ void lz77_gpu_set_host_chunk(long bytes)
     g.host_chunk = bytes > 0 ? bytes : (1ll << 62);
 }
 
+void lz77_gpu_set_history(int enabled) { g.history = enabled != 0; }
+
 int lz77_gpu_set_jump_piece(long bytes)
 {
     if (bytes != 0 && (bytes < (1L << 20) || bytes > (256L << 20))) return LZ77_E_ARG;
@@ -358,7 +361,7 @@ int lz77_gpu_encode_device(const void *d_in, long n_in, int sb, int la, void *d_
 
     unsigned long long *d_total = nullptr;
     StageEvents se = {{g.ev[0], g.ev[1], g.ev[2], g.ev[3]}};
-    CK(launch_encode((const uint8_t *)d_in, n_in, P, g.scratch, (uint32_t *)d_out, &d_total,
+    CK(launch_encode((const uint8_t *)d_in, n_in, 0, P, g.scratch, (uint32_t *)d_out, &d_total,
                      g.stream, g.timing ? &se : nullptr));
     CK(cudaMemcpyAsync(g.pinned, d_total, 8, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -433,15 +436,15 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
                 // tail of one overlaps the head of the next; scan + pack follow in order
                 cudaStream_t ps = (c & 1) ? g.aux2 : g.aux;
                 CK(cudaStreamWaitEvent(ps, ev_in[c], 0));
-                CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
+                CK(launch_encode_chunk((const uint8_t *)g.stage_in, 0, lo, len, c == 0, P, pl,
                                        (uint32_t *)g.stage_out, ps, nullptr, 1, nullptr));
                 CK(cudaEventRecord(ev_parse[c], ps));
                 CK(cudaStreamWaitEvent(g.hi, ev_parse[c], 0));
-                CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
+                CK(launch_encode_chunk((const uint8_t *)g.stage_in, 0, lo, len, c == 0, P, pl,
                                        (uint32_t *)g.stage_out, g.hi, nullptr, 2, &g.pinned_totals_dev[c]));
             } else {
                 CK(cudaStreamWaitEvent(g.hi, ev_in[c], 0));
-                CK(launch_encode_chunk((const uint8_t *)g.stage_in, lo, len, c == 0, P, pl,
+                CK(launch_encode_chunk((const uint8_t *)g.stage_in, 0, lo, len, c == 0, P, pl,
                                        (uint32_t *)g.stage_out, g.hi, nullptr, 0, &g.pinned_totals_dev[c]));
             }
             CK(cudaEventRecord(ev_done[c], g.hi));

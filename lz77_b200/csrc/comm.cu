@@ -346,13 +346,17 @@ int lz77_gpu_encode_sharded_device(const void *d_in, long n_in, int sb, int la, 
         else if ((size_t)out_cap < round16((size_t)lz77_gpu_encode_bound(n_in, P.sb, P.la)))
             arg = LZ77_E_SPACE;
         meta[0] = (unsigned long long)n_in;
-        meta[1] = arg == LZ77_OK ? ((unsigned long long)P.sb | ((unsigned long long)P.la << 16)) : 0;
+        meta[1] = arg == LZ77_OK ? ((unsigned long long)P.sb | ((unsigned long long)P.la << 16) |
+                                    ((unsigned long long)P.history << 32))
+                                 : 0;
         meta[2] = (unsigned long long)(long long)arg;
     }
     if ((rc = bcast_u64(c, meta, 3, root))) return rc;
     if ((long long)meta[2] != 0) return (int)(long long)meta[2];
     const long long N = (long long)meta[0];
-    if (make_params((int)(meta[1] & 0xffff), (int)(meta[1] >> 16), &P) != LZ77_OK) return LZ77_E_ARG;
+    if (make_params((int)(meta[1] & 0xffff), (int)((meta[1] >> 16) & 0xffff), &P) != LZ77_OK)
+        return LZ77_E_ARG;
+    P.history = (int)((meta[1] >> 32) & 1);  // root's setting counts
     const int T = P.tbits, world = c.world, rank = c.rank;
 
     // 2. runs of whole blocks; every rank allocates, then all agree to go on
@@ -360,9 +364,16 @@ int lz77_gpu_encode_sharded_device(const void *d_in, long n_in, int sb, int la, 
     for (int r = 0; r < world; r++) shard_range(N, world, P.block, r, &lo[r], &hi[r]);
     const long long len = hi[rank] - lo[rank];
     const bool direct = rank == root && lo[rank] == 0;  // root's run is the head of the stream
+    // history mode (lz77_gpu_set_history on root; it travels in the job): a run also needs
+    // the window in front of it, so the scatter sends that halo along
+    long long halo[kMaxDevices];
+    for (int r = 0; r < world; r++) {
+        const long long want = P.history ? (long long)((P.window + 15) & ~15) : 0;
+        halo[r] = lo[r] < want ? lo[r] : want;
+    }
     const size_t my_bound = round16((size_t)lz77_gpu_encode_bound(len, P.sb, P.la));
     rc = LZ77_OK;
-    if (rank != root) rc = grow(&c.stage_in, &c.stage_in_cap, (size_t)len + 64);
+    if (rank != root) rc = grow(&c.stage_in, &c.stage_in_cap, (size_t)(len + halo[rank]) + 64);
     if (!rc && !direct) rc = grow(&c.stage_out, &c.stage_out_cap, my_bound + 64);
     if (!rc) rc = grow(&c.scratch, &c.scratch_cap, encode_scratch_bytes(len, P));
     if ((rc = agree(c, rc))) return rc;
@@ -373,22 +384,25 @@ int lz77_gpu_encode_sharded_device(const void *d_in, long n_in, int sb, int la, 
     if (rank == root) {
         for (int r = 0; r < world; r++)
             if (r != root && hi[r] > lo[r]) {
-                NK(nc.Send((const char *)d_in + lo[r], (size_t)(hi[r] - lo[r]), kNcclUint8, r, comm, st));
-                c.comm_last.sent_bytes += (long)(hi[r] - lo[r]);
+                NK(nc.Send((const char *)d_in + lo[r] - halo[r], (size_t)(hi[r] - lo[r] + halo[r]),
+                           kNcclUint8, r, comm, st));
+                c.comm_last.sent_bytes += (long)(hi[r] - lo[r] + halo[r]);
             }
     } else if (len > 0) {
-        NK(nc.Recv(c.stage_in, (size_t)len, kNcclUint8, root, comm, st));
-        c.comm_last.recv_bytes += (long)len;
+        NK(nc.Recv(c.stage_in, (size_t)(len + halo[rank]), kNcclUint8, root, comm, st));
+        c.comm_last.recv_bytes += (long)(len + halo[rank]);
     }
     NK(nc.GroupEnd());
     c.comm_last.collectives++;
     tm.mark(1);
 
     // 4. every rank encodes its run
-    const uint8_t *src = rank == root ? (const uint8_t *)d_in + lo[rank] : (const uint8_t *)c.stage_in;
+    const uint8_t *src = rank == root ? (const uint8_t *)d_in + lo[rank]
+                                      : (const uint8_t *)c.stage_in + halo[rank];
+    const long long pre = rank == root ? lo[rank] : halo[rank];
     uint32_t *dst = direct ? (uint32_t *)d_out : (uint32_t *)c.stage_out;
     unsigned long long *d_total = nullptr;
-    CK(launch_encode(src, len, P, c.scratch, dst, &d_total, st, nullptr));
+    CK(launch_encode(src, len, pre, P, c.scratch, dst, &d_total, st, nullptr));
     tm.mark(2);
 
     // 5. token counts -> bit offset of every payload: 32 + T * sum(K_before)

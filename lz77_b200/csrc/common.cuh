@@ -26,6 +26,8 @@ struct Params {
     int block_shift;
     int tile_shift;    // decode tile = min(block, 128 KiB): what fits shared memory (a
                        // 512 KiB block is decoded as four tiles)
+    int history;       // encoder: 1 = the match window slides across block seams like the
+                       // reference's (lz77.c:101-105); 0 = independent blocks
 };
 
 __host__ __device__ inline int bitof(int n)  // bitio.c:41-43 in integers

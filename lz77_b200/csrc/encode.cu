@@ -268,12 +268,14 @@ long long encode_chunk_granule() { return 524288; }
 // phase 0: everything; phase 1: the search/parse kernel only; phase 2: the token
 // count scan and the bit-packer only (the host pipeline runs the searches of
 // consecutive chunks on alternating streams so their tails overlap).
-cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
-                                bool first, const Params &P, const EncodePlan &pl,
+cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long pre_base, long long lo,
+                                long long n_chunk, bool first, const Params &P,
+                                const EncodePlan &pl,
                                 uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
                                 int phase, unsigned long long *host_total)
 {
     const uint8_t *d_in = d_in_base + lo;
+    const long long pre = P.history ? pre_base + lo : 0;  // the earlier chunks are history
     const long long seg0 = lo / kSegBytes;
     const long long n_seg = (n_chunk + kSegBytes - 1) / kSegBytes;
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
@@ -289,11 +291,11 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
         // searched by an earlier phase-1 call
     } else if (n_chunk > 0 && P.window <= 8191) {
         // small windows: bucketed search (search_bucket.cu)
-        cudaError_t rc = launch_parse_bucket(d_in, n_chunk, P, tok_tmp, seg_ntok, st);
+        cudaError_t rc = launch_parse_bucket(d_in, n_chunk, pre, P, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
     } else if (n_chunk > 0) {
         // large windows: block-level buckets (search_bigwin.cu)
-        cudaError_t rc = launch_parse_bigwin(d_in, n_chunk, P, pl.big, tok_tmp, seg_ntok, st);
+        cudaError_t rc = launch_parse_bigwin(d_in, n_chunk, pre, P, pl.big, tok_tmp, seg_ntok, st);
         if (rc != cudaSuccess) return rc;
     }
     if (ev) cudaEventRecord(ev->e[1], st);
@@ -320,13 +322,13 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long lon
     return cudaGetLastError();
 }
 
-cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, void *scratch,
-                          uint32_t *d_out_words, unsigned long long **d_total_tokens,
-                          cudaStream_t st, StageEvents *ev)
+cudaError_t launch_encode(const uint8_t *d_in, long long n_in, long long pre, const Params &P,
+                          void *scratch, uint32_t *d_out_words,
+                          unsigned long long **d_total_tokens, cudaStream_t st, StageEvents *ev)
 {
     const EncodePlan pl = encode_plan(scratch, n_in, P);
     *d_total_tokens = pl.total;
-    return launch_encode_chunk(d_in, 0, n_in, true, P, pl, d_out_words, st, ev, 0, nullptr);
+    return launch_encode_chunk(d_in, pre, 0, n_in, true, P, pl, d_out_words, st, ev, 0, nullptr);
 }
 
 int encode_launch_count(long long n_in)

@@ -14,9 +14,10 @@ size_t encode_scratch_bytes(long long n_in, const Params &P);
 int encode_launch_count(long long n_in);
 // d_out_words must hold 4 + ceil(n_in * T / 8) bytes rounded up to 16.
 // *d_total_tokens receives a device pointer (inside scratch) to the token count.
-cudaError_t launch_encode(const uint8_t *d_in, long long n_in, const Params &P, void *scratch,
-                          uint32_t *d_out_words, unsigned long long **d_total_tokens,
-                          cudaStream_t st, StageEvents *ev);
+// `pre`: valid input bytes in front of d_in (history mode only; 0 otherwise)
+cudaError_t launch_encode(const uint8_t *d_in, long long n_in, long long pre, const Params &P,
+                          void *scratch, uint32_t *d_out_words,
+                          unsigned long long **d_total_tokens, cudaStream_t st, StageEvents *ev);
 
 // chunked encoding (the host entry point overlaps copies with kernels)
 struct EncodePlan {
@@ -29,20 +30,23 @@ struct EncodePlan {
 };
 EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P);
 long long encode_chunk_granule();
-cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long lo, long long n_chunk,
-                                bool first, const Params &P, const EncodePlan &pl,
+cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long pre_base, long long lo,
+                                long long n_chunk, bool first, const Params &P,
+                                const EncodePlan &pl,
                                 uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
                                 int phase, unsigned long long *host_total);
 
 // bucketed longest-match search + greedy parse (search_bucket.cu)
-cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
-                                uint32_t *tok_tmp, uint32_t *seg_ntok, cudaStream_t st);
+// `pre`: valid input bytes in front of d_in (history mode reaches back into them)
+cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long pre,
+                                const Params &P, uint32_t *tok_tmp, uint32_t *seg_ntok,
+                                cudaStream_t st);
 
 // large windows: block-level buckets (search_bigwin.cu)
 size_t bigwin_scratch_bytes(long long n_in, const Params &P);
-cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Params &P,
-                                void *scratch, uint32_t *tok_tmp, uint32_t *seg_ntok,
-                                cudaStream_t st);
+cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, long long pre,
+                                const Params &P, void *scratch, uint32_t *tok_tmp,
+                                uint32_t *seg_ntok, cudaStream_t st);
 
 void bigwin_release(int device);  // side stream + events of the large-window encoder
 

@@ -205,9 +205,10 @@ constexpr int kBigWarps = 16;
 
 template <bool kSmallLA>
 __global__ void __launch_bounds__(kBigWarps * 32, 2)
-lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
-                         const uint32_t *__restrict__ sorted, const uint32_t *__restrict__ bstart,
-                         uint32_t *__restrict__ tok_tmp, uint32_t *__restrict__ seg_ntok)
+lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, long long pre, int lead,
+                         Params P, int hist_cap, const uint32_t *__restrict__ sorted,
+                         const uint32_t *__restrict__ bstart, uint32_t *__restrict__ tok_tmp,
+                         uint32_t *__restrict__ seg_ntok)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
@@ -219,7 +220,9 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
     const long long blk_i = tile_lo >> P.block_shift;
     const long long blk_lo = blk_i << P.block_shift;
 
-    long long hist = tile_lo - blk_lo;
+    // independent blocks: the window starts at the block; history mode: it slides across
+    // block seams into the `pre` valid bytes in front of `in` (lz77.c:101-105)
+    long long hist = P.history ? tile_lo + pre : tile_lo - blk_lo;
     if (hist > P.window) hist = P.window;
     const int hist_al = (int)((hist + 15) & ~15LL);
     const long long src_lo = tile_lo - hist_al;
@@ -251,8 +254,16 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
     const int seg_end = (int)(seg_hi - src_lo) + dst0;
     int p0 = (int)(seg_lo - src_lo) + dst0;
     const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // smem index of block byte 0 (may be < 0)
-    const uint32_t *blk_sorted = sorted + blk_lo;
-    const uint32_t *blk_bstart = bstart + blk_i * (kBigBuckets + 1);
+    const int first_idx = dst0 + hist_al - (int)hist;   // oldest byte a match may start at
+    // bucket tables of this block and (history mode) of the block in front of it; table
+    // slot 0 belongs to the `lead` block sorted in front of the piece
+    const long long slot = blk_i + lead;
+    const uint32_t *blk_sorted = sorted + (slot << P.block_shift);
+    const uint32_t *blk_bstart = bstart + slot * (kBigBuckets + 1);
+    const bool has_prev = P.history && slot >= 1 && first_idx < blk_idx;
+    const uint32_t *prev_sorted = blk_sorted - (1LL << P.block_shift);
+    const uint32_t *prev_bstart = blk_bstart - (kBigBuckets + 1);
+    const int prev_idx = blk_idx - (int)(1LL << P.block_shift);  // smem index of its byte 0
     uint32_t *const tok_row = tok_tmp + sgm * kSegBytes;
     uint32_t *tok_at = tok_row;  // one 4-byte store per token by one lane (L2 merges the sectors)
     const int len_shift = P.ob, lit_shift = P.ob + P.lb;
@@ -260,7 +271,7 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
 
     while (p0 < seg_end) {
         const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
-        const int reach = min(p0 - blk_idx, window);    // lz77.c:101-105
+        const int reach = min(p0 - first_idx, window);  // lz77.c:101-105
         int len = 0, off = 0;
 
         if (max_len > 0 && reach > 0) {
@@ -280,24 +291,35 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             int best_len = 0, best_q = 0;
             if (max_len >= 2) {
                 const int key = big_key(b0, tgt[0] >> 8);
-                const int bs = (int)__ldg(blk_bstart + key);
-                const int bn = (int)__ldg(blk_bstart + key + 1) - bs;
-                const uint32_t *e = blk_sorted + bs;
-                // bucket entries are positions in the block; smem index = entry + blk_idx
-                const int lo_blk = lo_idx - blk_idx, p_blk = p0 - blk_idx;
-                int i = bn <= 64 ? 0 : warp_lower_bound_g(e, bn, lo_blk, lane);
-                for (; i < bn; i += 32) {
-                    const int idx = i + lane;
-                    const int qb = idx < bn ? (int)__ldg(e + idx) : 0x7fffffff;
-                    const bool in = qb >= lo_blk && qb < p_blk;
-                    const int q = qb + blk_idx;
-                    const int l = round_match_len_big<kSmallLA>(smem, q, in, p0, tgt, max_len);
-                    if (l > best_len) {  // nearer than anything this lane has seen: longer
-                        best_len = l;
-                        best_q = q;
+                // one bucket list: entries are positions in their block, ascending; smem
+                // index = entry + base_idx
+                auto scan_list = [&](const uint32_t *list, const uint32_t *starts, int base_idx) {
+                    const int bs = (int)__ldg(starts + key);
+                    const int bn = (int)__ldg(starts + key + 1) - bs;
+                    const uint32_t *e = list + bs;
+                    const int lo_blk = lo_idx - base_idx, p_blk = p0 - base_idx;
+                    int i = bn <= 64 ? 0 : warp_lower_bound_g(e, bn, lo_blk, lane);
+                    for (; i < bn; i += 32) {
+                        const int idx = i + lane;
+                        const int qb = idx < bn ? (int)__ldg(e + idx) : 0x7fffffff;
+                        const bool in = qb >= lo_blk && qb < p_blk;
+                        const int q = in ? qb + base_idx : 0;
+                        const int l = round_match_len_big<kSmallLA>(smem, q, in, p0, tgt, max_len);
+                        if (l > best_len) {  // nearer than anything this lane has seen: longer
+                            best_len = l;
+                            best_q = q;
+                        }
+                        if (__any_sync(0xffffffffu, best_len >= max_len || qb >= p_blk)) break;
                     }
-                    if (__any_sync(0xffffffffu, best_len >= max_len || qb >= p_blk)) break;
+                };
+                // oldest first: the tail of the previous block's list, then this block's
+                // (not needed once a maximum-length match is in: a later one is not longer)
+                bool full = false;
+                if (has_prev && lo_idx < blk_idx) {
+                    scan_list(prev_sorted, prev_bstart, prev_idx);
+                    full = __any_sync(0xffffffffu, best_len >= max_len);
                 }
+                if (!full) scan_list(blk_sorted, blk_bstart, blk_idx);
             }
             // (no candidate: length 0 in the top bits, the start is not used)
             const uint32_t k = __reduce_max_sync(
@@ -349,7 +371,8 @@ constexpr long long kBigPiece = 64ll << 20;  // bucket tables are built for this
 
 static size_t bigwin_piece_scratch(long long n_in, const Params &P)
 {
-    const long long n_blocks = (n_in + P.block - 1) >> P.block_shift;
+    // (history mode sorts one more block in front of every piece)
+    const long long n_blocks = ((n_in + P.block - 1) >> P.block_shift) + (P.history ? 1 : 0);
     const long long npos = n_blocks << P.block_shift;
     return ((size_t)npos * 4 * 2 + (size_t)n_blocks * (kBigBuckets + 1) * 4 + 4095) & ~(size_t)4095;
 }
@@ -409,9 +432,9 @@ void bigwin_release(int device)
 // d_in points at a block boundary.  The input is handled in pieces of kBigPiece
 // bytes: the block sort of piece k+1 runs on a high-priority side stream while
 // piece k is parsed on `st` (two sets of tables in the scratch area).
-cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Params &P,
-                                void *scratch, uint32_t *tok_tmp, uint32_t *seg_ntok,
-                                cudaStream_t st)
+cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, long long pre,
+                                const Params &P, void *scratch, uint32_t *tok_tmp,
+                                uint32_t *seg_ntok, cudaStream_t st)
 {
     if (n_in <= 0) return cudaSuccess;
     BigwinStreams *bwp = nullptr;
@@ -436,19 +459,23 @@ cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, const Param
     for (long long o = 0; o < n_in; o += kBigPiece, k++) {
         const long long len = n_in - o < kBigPiece ? n_in - o : kBigPiece;
         const int buf = (int)(k & 1);
-        const long long n_blocks = (len + P.block - 1) >> P.block_shift;
+        // history mode: the block in front of the piece is sorted along with it, so the
+        // first block of the piece finds the candidates of its window there
+        const int lead = (P.history && pre + o >= P.block) ? 1 : 0;
+        const long long n_blocks = ((len + P.block - 1) >> P.block_shift) + lead;
         const long long npos = n_blocks << P.block_shift;
         uint32_t *sorted = (uint32_t *)((char *)scratch + buf * piece_scratch);
         uint32_t *tmp = sorted + npos;
         uint32_t *bstart = tmp + npos;
         if (k >= 2) cudaStreamWaitEvent(g_bw.sort, g_bw.parsed[buf], 0);  // tables free again
         lz77_block_sort_kernel<<<(unsigned)n_blocks, kSortThreads, sort_smem, g_bw.sort>>>(
-            d_in + o, len, P.block_shift, sorted, tmp, bstart);
+            d_in + o - lead * P.block, len + lead * P.block, P.block_shift, sorted, tmp, bstart);
         cudaEventRecord(g_bw.sorted[buf], g_bw.sort);
         cudaStreamWaitEvent(st, g_bw.sorted[buf], 0);
         const long long n_tiles = (len + tile_bytes - 1) / tile_bytes;
         parse<<<(unsigned)n_tiles, kBigWarps * 32, parse_smem, st>>>(
-            d_in + o, len, P, hist_cap, sorted, bstart, tok_tmp + o, seg_ntok + o / kSegBytes);
+            d_in + o, len, pre + o, lead, P, hist_cap, sorted, bstart, tok_tmp + o,
+            seg_ntok + o / kSegBytes);
         cudaEventRecord(g_bw.parsed[buf], st);
     }
     return cudaGetLastError();

@@ -197,8 +197,8 @@ __device__ __forceinline__ int group_lower_bound_s(uint32_t se, int n, int lo, i
 #endif
 template <bool kSmallLA, int kWarps, int kLanes, typename PosT, bool kSortedGlobal>
 __global__ void __launch_bounds__(kWarps * 32, LZ77_PARSE_MINBLOCKS)
-lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, int hist_cap,
-                         long long n_tiles, uint32_t *__restrict__ tok_tmp,
+lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long pre, Params P,
+                         int hist_cap, long long n_tiles, uint32_t *__restrict__ tok_tmp,
                          uint32_t *__restrict__ seg_ntok, PosT *sorted_global,
                          long long sorted_stride)
 {
@@ -239,7 +239,9 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
     uint32_t phase = 0;
     for (long long tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x, phase ^= 1u) {
         const long long tile_lo = tile_i * tile_bytes;
-        const long long blk_lo = (tile_lo >> P.block_shift) << P.block_shift;
+        // the window starts at the block (independent blocks) or, in history mode, reaches
+        // back across block seams into the `pre` valid bytes in front of `in`
+        const long long blk_lo = P.history ? -pre : (tile_lo >> P.block_shift) << P.block_shift;
 
         // ---- stage history + tile with one TMA bulk copy -------------------
         long long hist = tile_lo - blk_lo;
@@ -356,7 +358,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
             if (seg_hi > n) seg_hi = n;
             const int seg_end = (int)(seg_hi - src_lo) + dst0;
             int p0 = (int)(seg_lo - src_lo) + dst0;
-            const int blk_idx = (int)(blk_lo - src_lo) + dst0;  // may be < 0
+            const int first_idx = dst0 + hist_al - (int)hist;  // oldest byte a match may start at
             uint32_t *tok_row = tok_tmp + sgm * kSegBytes;
             const int len_shift = P.ob, lit_shift = P.ob + P.lb;
             const int la = P.la, window = P.window;
@@ -364,7 +366,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
 
             while (p0 < seg_end) {
                 const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
-                const int reach = min(p0 - blk_idx, window);    // lz77.c:101-105
+                const int reach = min(p0 - first_idx, window);  // lz77.c:101-105
                 int len = 0, off = 0;
 
                 if (max_len > 0 && reach > 0) {
@@ -487,8 +489,9 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, Params P, 
 #define LZ77_PARSE_LANES 32
 #endif
 
-cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Params &P,
-                                uint32_t *tok_tmp, uint32_t *seg_ntok, cudaStream_t st)
+cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long pre,
+                                const Params &P, uint32_t *tok_tmp, uint32_t *seg_ntok,
+                                cudaStream_t st)
 {
     constexpr int kW = LZ77_PARSE_WARPS, kL = LZ77_PARSE_LANES;
     const bool small_la = P.la <= 16;
@@ -506,7 +509,7 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, const Param
     cudaError_t rc =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
-    kern<<<(unsigned)n_tiles, kW * 32, smem, st>>>(d_in, n_in, P, hist_cap, n_tiles, tok_tmp,
+    kern<<<(unsigned)n_tiles, kW * 32, smem, st>>>(d_in, n_in, pre, P, hist_cap, n_tiles, tok_tmp,
                                                    seg_ntok, (uint16_t *)nullptr, 0);
     return cudaGetLastError();
 }

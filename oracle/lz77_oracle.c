@@ -519,11 +519,14 @@ long lz77o_segmented_encode(const uint8_t *in, long n_in, int sb, int la,
     const int LA = (la == -1) ? LZ77O_DEFAULT_LA : la;
     if (SB < 1 || SB > 65535 || LA < 1 || LA > 65535 || n_in < 0)
         return LZ77O_E_ARG;
-    if (block <= 0)
+    /* block <= 0: ONE block, i.e. the reference's sliding window over the whole input
+     * (lz77.c:101-105) -- with segment > 0 the stream of the GPU encoder's history mode */
+    const int one_block = block <= 0;
+    if (one_block)
         block = n_in > 0 ? n_in : 1;
     if (segment <= 0 || segment > block)
         segment = block;
-    if (block % segment != 0)
+    if (!one_block && block % segment != 0)
         return LZ77O_E_ARG;
 
     const int off_bits = lz77o_bitof(SB);

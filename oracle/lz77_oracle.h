@@ -79,7 +79,10 @@ long lz77o_blocked_encode(const uint8_t *in, long n_in, int sb, int la,
  * token never runs past the end of its segment; the match WINDOW still spans
  * the whole block).  segment must divide block; segment <= 0 means no restarts.
  * The GPU encoder uses block = lz77_gpu_block_size(sb), segment =
- * lz77_gpu_segment_size(); parity with it is byte-for-byte.
+ * lz77_gpu_segment_size(); parity with it is byte-for-byte.  block <= 0 with
+ * segment > 0 is the GPU encoder's history mode (lz77_gpu_set_history): the window
+ * slides over the whole input like the reference's (lz77.c:101-105), only the parse
+ * restarts remain.
  */
 long lz77o_segmented_encode(const uint8_t *in, long n_in, int sb, int la,
                             long block, long segment, uint8_t *out,

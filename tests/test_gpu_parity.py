@@ -583,3 +583,70 @@ def test_token_array_helpers(lz, orc, sb, la):
         lz.token_at_tensor(s, len(data) + 1)
     with pytest.raises(lz.Lz77Error):
         lz.slice_tokens_tensor(s, 0, k + 1)
+
+
+# ---- history mode: the window slides across block seams ----
+
+@pytest.fixture
+def history(lz):
+    from lz77_b200 import api
+    api.set_history(True)
+    yield api
+    api.set_history(False)
+
+
+def _history_input(kind, sb):
+    from lz77_b200 import synth
+    # several blocks, a ragged tail: 64 KiB blocks below SB 8192, 512 KiB above
+    n = (5 * 65536 + 12_345) if sb <= 8191 else (2 * 524288 + 300_001)
+    if kind == "zeros":
+        n = min(n, 200_000)
+    return synth.make(kind, n, seed=31).numpy().tobytes()
+
+
+@pytest.mark.parametrize("sb,la", PARAM_SETS)
+@pytest.mark.parametrize("kind", ["zipf_text", "random", "zeros", "log_like"])
+def test_history_mode_equals_specification(lz, orc, history, sb, la, kind):
+    """lz77_gpu_set_history(1): byte-identical to the oracle's one-block specification
+    (the reference's sliding window, lz77.c:101-105, with the parse restarts), decodable
+    by the reference decoder's restatement and by the GPU (pointer jumping)."""
+    data = _history_input(kind, sb)
+    enc = lz.encode(data, la=la, sb=sb)
+    spec, ntok = orc.blocked_encode(data, sb, la, 0, lz.segment_size())
+    assert enc == spec
+    assert orc.decode(enc) == data
+    assert lz.decode(enc) == data
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (65535, 255), (1000, 20)])
+def test_history_mode_host_chunks_and_reference_decoder(lz, orc, history, ref_available, sb, la):
+    """The chunked host pipeline in history mode (every chunk's window reaches into the
+    chunk before it) gives the one-call stream; the compiled reference decodes it."""
+    from lz77_b200 import synth
+    data = synth.zipf_text(3 * (1 << 20) + 4321, seed=32).numpy().tobytes()
+    one = lz.encode(data, la=la, sb=sb)
+    history.set_host_chunk(1 << 20)
+    try:
+        chunked = lz.encode(data, la=la, sb=sb)
+    finally:
+        history.set_host_chunk(16 << 20)
+    assert chunked == one
+    spec, _ = orc.blocked_encode(data, sb, la, 0, lz.segment_size())
+    assert one == spec
+    if ref_available:
+        from oracle import ref_run
+        assert ref_run("-d", one) == data
+
+
+@pytest.mark.parametrize("kind", ["zipf_text", "random"])
+def test_history_mode_ratio_within_half_percent_of_reference(lz, orc, history, kind):
+    """SB 65535 / LA 255: with the window sliding across block seams the stream is within
+    0.5 % of the reference encoder's (what is left is the parse restart per KiB)."""
+    from lz77_b200 import synth
+    data = synth.make(kind, 3 << 20, seed=33).numpy().tobytes()
+    ours = len(lz.encode(data, la=255, sb=65535))
+    ref = len(orc.ref_encode(data, 65535, 255))
+    assert ours <= ref * 1.005, (ours, ref, ours / ref)
+    history.set_history(False)
+    blocked = len(lz.encode(data, la=255, sb=65535))
+    assert blocked >= ours
