@@ -46,17 +46,45 @@ UNIT = "GB/s"
 # helpers
 # --------------------------------------------------------------------------- #
 
-def ncu_traffic(kernel: str, n_bytes: int):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture
-    (profiles/traffic.json), valid only for the workload size it was taken on."""
+def csrc_sha16() -> str:
+    """Hash of the kernel sources: the ncu figures in profiles/traffic.json are only
+    reported while they describe the kernels that are actually running."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "lz77_b200" / "csrc").glob("*.cu*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_figure(key: str, n_bytes: int):
+    """A per-launch figure (DRAM bytes, executed warp instructions) of the committed ncu
+    capture, profiles/traffic.json: valid only for the workload size AND the kernel
+    sources (csrc_sha16) it was taken on -- otherwise None (stale numbers are not reported)."""
     p = ROOT / "profiles" / "traffic.json"
     try:
         t = json.loads(p.read_text())
-        if int(t.get("workload_bytes", -1)) == int(n_bytes):
-            return int(t[kernel])
+        if int(t.get("workload_bytes", -1)) == int(n_bytes) and t.get("csrc_sha16") == csrc_sha16():
+            return int(t[key])
     except Exception:
         pass
     return None
+
+
+def issue_bound(kernel: str, n_bytes: int, tokens: int, measured_ms: float, clocks: dict):
+    """The second bound of a kernel whose tokens are a few bytes each: instruction issue.
+    warp instructions per launch (ncu smsp__inst_executed.sum, profiles/traffic.json) over
+    148 SMs x 4 schedulers x the SM clock sampled during the run = the time the kernel
+    needs if every scheduler issued every cycle."""
+    inst = ncu_figure(kernel + ".inst_executed", n_bytes)
+    mhz = (clocks or {}).get("sm_mhz")
+    if not inst or not mhz:
+        return None
+    slots_per_ms = 148 * 4 * mhz * 1e3
+    min_ms = inst / slots_per_ms
+    return {"warp_inst_per_launch": inst, "warp_inst_per_token": inst / max(tokens, 1),
+            "issue_slots_per_ms": slots_per_ms, "min_ms": min_ms,
+            "frac": min_ms / measured_ms if measured_ms else None}
 
 
 def measured_peak_gbs():
@@ -69,11 +97,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def bind_near_gpu(local_rank: int) -> None:
+def bind_near_gpu(local_rank: int) -> dict:
     """One process per GPU: run on the CPUs next to this rank's GPU, so that the pinned
     host buffers of the end-to-end leg are allocated on the GPU's NUMA node (with several
     ranks on one socket's memory the H2D / D2H copies share its bandwidth).  Best effort:
-    any failure leaves the affinity as it was."""
+    any failure leaves the affinity as it was.  Returns what happened (on a box that
+    reports every GPU next to the same CPUs the binding changes nothing)."""
+    before = len(os.sched_getaffinity(0))
     try:
         import pynvml
         import torch
@@ -86,8 +116,11 @@ def bind_near_gpu(local_rank: int) -> None:
         cpus &= os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
+        after = len(os.sched_getaffinity(0))
+        return {"cpus_before": before, "cpus_after": after, "changed": after != before}
     except Exception as e:  # noqa: BLE001
         print(f"[bench] no NUMA binding for rank {local_rank}: {e}", file=sys.stderr)
+        return {"cpus_before": before, "cpus_after": before, "changed": False, "error": str(e)}
 
 
 class ClockSampler:
@@ -250,6 +283,42 @@ def run_reference(args):
 # this framework
 # --------------------------------------------------------------------------- #
 
+def run_cli(src_tensor, sb: int, la: int, gpus: int):
+    """The drop-in surface (main.c:141-169): `lz77 -c` / `lz77 -d` file to file on tmpfs
+    for the bench workload.  Two figures each way: the whole process (CUDA context
+    creation and pinned allocations included) and the codec loop alone as the program
+    reports it with -v (read + GPU + write overlapped)."""
+    import re
+    exe = ROOT / "lz77_b200" / "bin" / "lz77"
+    if not exe.exists():
+        return {"unavailable": "lz77_b200/bin/lz77 is not built"}
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    rec = {"gpus": gpus, "files": "tmpfs"}
+    with tempfile.TemporaryDirectory(dir=tmp) as d:
+        fin, flz, fout = (os.path.join(d, x) for x in ("in.bin", "out.lz", "back.bin"))
+        src_tensor.cpu().numpy().tofile(fin)
+        n = os.path.getsize(fin)
+        extra = ["-G", str(gpus)] if gpus > 1 else []
+        for mode, a, b, key in (("-c", fin, flz, "encode"), ("-d", flz, fout, "decode")):
+            best_wall, steady = None, None
+            for _ in range(2):   # the second run has the files in the page cache
+                t0 = time.perf_counter()
+                r = subprocess.run([str(exe), mode, "-i", a, "-o", b, "-s", str(sb), "-l", str(la),
+                                    "-v", *extra], capture_output=True, text=True)
+                dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return {"unavailable": f"lz77 {mode} failed: {r.stderr.strip()[:200]}"}
+                m = re.search(r"in ([0-9.]+) s \(([0-9.]+) GB/s", r.stderr)
+                if best_wall is None or dt < best_wall:
+                    best_wall, steady = dt, (float(m.group(2)) if m else None)
+            rec[key + "_wall_s"] = best_wall
+            rec[key + "_gbs_process"] = n / best_wall / 1e9
+            rec[key + "_gbs_codec_loop"] = steady
+        rec["stream_bytes"] = os.path.getsize(flz)
+        rec["roundtrip_exact"] = open(fin, "rb").read() == open(fout, "rb").read()
+    return rec
+
+
 def sharded_workload(world: int):
     """ONE input resident on rank 0, cut into runs of whole blocks over all ranks (NCCL
     scatter -> per-rank encode -> gather into ONE stream -> sharded decode)."""
@@ -358,8 +427,7 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: this codec has no CPU path")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        bind_near_gpu(local_rank)
+    numa = bind_near_gpu(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
@@ -391,7 +459,10 @@ def run_native(args):
     out_buf = torch.empty((n + 15) & ~15, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
 
-    stream_t = torch.cuda.current_stream(dev)
+    # the library runs its kernels on this stream, and the timing events are recorded on it
+    # (torch's default stream has handle 0, which the library would replace by its own)
+    stream_t = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream_t)
     api.set_stream(stream_t.cuda_stream)
 
     def barrier():
@@ -451,23 +522,86 @@ def run_native(args):
         m = api.decode_into(h_stream.ptr, c, h_out.ptr, n)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_enc_s = e2e_dec_s = 0.0
     e0.record(stream_t)
     for _ in range(e2e_steps):
+        # (both calls are host-synchronous: the result is in host memory on return)
+        t0 = time.perf_counter()
         c = api.encode_into(h_in.ptr, n, h_stream.ptr, cap, la=la, sb=sb)
+        t1 = time.perf_counter()
         m = api.decode_into(h_stream.ptr, c, h_out.ptr, n)
+        t2 = time.perf_counter()
+        e2e_enc_s += t1 - t0
+        e2e_dec_s += t2 - t1
     e1.record(stream_t)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    e2e_enc_ms, e2e_dec_ms = e2e_enc_s / e2e_steps * 1e3, e2e_dec_s / e2e_steps * 1e3
     assert m == n and bytes(h_out.array[:4096]) == bytes(h_in.array[:4096])
     assert (h_out.array[:n] == h_in.array[:n]).all(), "e2e roundtrip mismatch"
 
+    # ---- the ceiling of that leg: the same bytes as plain pinned copies, H2D and D2H
+    #      side by side on two streams (what a codec that cost nothing would take) ----
+    p_in = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    p_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d_a = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(n, dtype=torch.uint8, device=dev)
+    s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def plain_copies():
+        with torch.cuda.stream(s_up):      # encode reads n, decode reads c
+            d_a.copy_(p_in, non_blocking=True)
+            d_a[:c_bytes].copy_(p_in[:c_bytes], non_blocking=True)
+        with torch.cuda.stream(s_down):    # encode returns c, decode returns n
+            p_out[:c_bytes].copy_(d_b[:c_bytes], non_blocking=True)
+            p_out.copy_(d_b, non_blocking=True)
+        s_up.synchronize()
+        s_down.synchronize()
+
+    plain_copies()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        plain_copies()
+    copy_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    barrier()
+    del p_in, p_out, d_a, d_b
+
+    # ---- history mode: the window slides across block seams (the reference's ratio);
+    #      such streams decode by pointer jumping, like streams of the reference encoder ----
+    api.set_history(True)
+    hs, hk = api.encode_tensor(src, la=la, sb=sb, out=stream_buf)
+    hist_bytes = hs.numel()
+    hb = api.decode_tensor(hs, out=out_buf)
+    assert torch.equal(hb, src), "history-mode roundtrip mismatch"
+    hist_enc, hist_dec = [], []
+    for _ in range(max(1, min(args.steps, 3))):
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a0.record(stream_t)
+        hs, hk = api.encode_tensor(src, la=la, sb=sb, out=stream_buf)
+        a1.record(stream_t)
+        hb = api.decode_tensor(hs, out=out_buf)
+        a2.record(stream_t)
+        torch.cuda.synchronize()
+        hist_enc.append(a0.elapsed_time(a1))
+        hist_dec.append(a1.elapsed_time(a2))
+    api.set_history(False)
+    hist_enc_ms, hist_dec_ms = statistics.median(hist_enc), statistics.median(hist_dec)
+    clocks = sampler.stop()
+
     # ---- max over ranks ----------------------------------------------------
-    times = torch.tensor([total_ms, enc_ms, dec_ms, e2e_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([total_ms, enc_ms, dec_ms, e2e_ms, e2e_enc_ms, e2e_dec_ms, copy_ms,
+                          hist_enc_ms, hist_dec_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, dec_ms, e2e_ms = times.tolist()
+    (total_ms, enc_ms, dec_ms, e2e_ms, e2e_enc_ms, e2e_dec_ms, copy_ms, hist_enc_ms,
+     hist_dec_ms) = times.tolist()
 
+    cli = None
+    if rank == 0 and not args.no_cli:
+        cli = run_cli(src, sb, la, 1)
+        if world > 1:
+            cli = {"one_gpu": cli, "all_gpus": run_cli(src, sb, la, world)}
     sharded = None
     if dist is not None and not args.no_sharded:
         del src, stream_buf, out_buf, s, back
@@ -498,23 +632,44 @@ def run_native(args):
             "kernel_ms": med,
             "e2e": {"value": world * n / (e2e_ms / e2e_steps * 1e-3) / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": n + c_bytes, "d2h_bytes_per_step": c_bytes + n,
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "encode_gbs": world * n / (e2e_enc_ms * 1e-3) / 1e9,
+                    "decode_gbs": world * n / (e2e_dec_ms * 1e-3) / 1e9,
+                    "encode_ms": e2e_enc_ms, "decode_ms": e2e_dec_ms,
+                    # the same H2D + D2H bytes as plain pinned copies on two streams, all
+                    # ranks at once: what the host memory system / PCIe allow this leg
+                    "copy_ceiling_gbs": world * n / (copy_ms * 1e-3) / 1e9,
+                    "copy_ceiling_ms": copy_ms,
+                    "frac_of_copy_ceiling": copy_ms / (e2e_ms / e2e_steps),
+                    "numa_binding": numa},
+            "history_mode": {"what": "lz77_gpu_set_history(1): window slides across block seams "
+                                     "(lz77.c:101-105); decode = pointer jumping (decode_jump.cu), "
+                                     "the path streams of the reference encoder take",
+                             "encode_gbs": world * n / (hist_enc_ms * 1e-3) / 1e9,
+                             "decode_gbs": world * n / (hist_dec_ms * 1e-3) / 1e9,
+                             "encode_ms": hist_enc_ms, "jump_decode_ms": hist_dec_ms,
+                             "ratio": n / hist_bytes,
+                             "jump_decode_hbm_frac": (n + hist_bytes) / (hist_dec_ms * 1e-3) / 1e9 / peak},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "lz77_parse_bucket_kernel (longest-match search + greedy parse)",
                          "bound": "hbm", "achieved": search_gbs, "peak": peak, "unit": "GB/s",
                          "frac": search_gbs / peak,
-                         "traffic": ncu_traffic("lz77_parse_bucket_kernel", n),
+                         "traffic": ncu_figure("lz77_parse_bucket_kernel", n),
                          "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes},
             "roofline_decode": {"kernel": "lz77_decode_tile_kernel (match copy)",
                                 "bound": "hbm", "achieved": copy_gbs, "peak": peak,
                                 "unit": "GB/s", "frac": copy_gbs / peak,
-                                "traffic": ncu_traffic("lz77_decode_tile_kernel", n),
-                                "algorithmic_bytes": alg_bytes},
+                                "traffic": ncu_figure("lz77_decode_tile_kernel", n),
+                                "algorithmic_bytes": alg_bytes,
+                                "issue_bound": issue_bound("lz77_decode_tile_kernel", n, k,
+                                                           med["dec_copy_ms"], clocks)},
         }
         if sharded is not None:
             line["sharded"] = sharded
+        if cli is not None:
+            line["cli"] = cli
         if not args.no_cpu_baseline:
             try:
                 ref = CpuReference(slice_bytes=args.ref_slice_mib << 20)
@@ -542,6 +697,7 @@ def main():
     ap.add_argument("--ref-slice-mib", type=int, default=8,
                     help="per-core slice the CPU reference encodes+decodes per sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the file-to-file CLI leg")
     ap.add_argument("--no-sharded", action="store_true",
                     help="N > 1: skip the one-input sharded leg (NCCL scatter/gather)")
     ap.add_argument("--sharded-steps", type=int, default=3)

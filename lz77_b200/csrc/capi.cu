@@ -370,7 +370,7 @@ int lz77_gpu_encode_device(const void *d_in, long n_in, int sb, int la, void *d_
     if (n_tokens) *n_tokens = (long)k;
 
     memset(&g.last, 0, sizeof g.last);
-    g.last.launches = encode_launch_count(n_in);
+    g.last.launches = encode_launch_count(n_in, P);
     g.last.n_tokens = (long)k;
     if (g.timing) {
         g.last.enc_search_ms = ms_between(g.ev[0], g.ev[1]);
@@ -437,15 +437,18 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
                 cudaStream_t ps = (c & 1) ? g.aux2 : g.aux;
                 CK(cudaStreamWaitEvent(ps, ev_in[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, 0, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, ps, nullptr, 1, nullptr));
+                                       (uint32_t *)g.stage_out, ps, nullptr, 1,
+                                       &g.pinned_totals_dev[c], (int)(c & 63)));
                 CK(cudaEventRecord(ev_parse[c], ps));
                 CK(cudaStreamWaitEvent(g.hi, ev_parse[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, 0, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, g.hi, nullptr, 2, &g.pinned_totals_dev[c]));
+                                       (uint32_t *)g.stage_out, g.hi, nullptr, 2,
+                                       &g.pinned_totals_dev[c], (int)(c & 63)));
             } else {
                 CK(cudaStreamWaitEvent(g.hi, ev_in[c], 0));
                 CK(launch_encode_chunk((const uint8_t *)g.stage_in, 0, lo, len, c == 0, P, pl,
-                                       (uint32_t *)g.stage_out, g.hi, nullptr, 0, &g.pinned_totals_dev[c]));
+                                       (uint32_t *)g.stage_out, g.hi, nullptr, 0,
+                                       &g.pinned_totals_dev[c], (int)(c & 63)));
             }
             CK(cudaEventRecord(ev_done[c], g.hi));
         }
@@ -479,7 +482,7 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         if (result != LZ77_OK) return result;
         *n_out = done_bytes;
         memset(&g.last, 0, sizeof g.last);
-        g.last.launches = (int)n_chunks * encode_launch_count(chunk);
+        g.last.launches = (int)n_chunks * encode_launch_count(chunk, P);
         g.last.n_tokens = (long)k;
         // pipelined call: the stages overlap, so only the span of the compute stream
         // (first H2D issued .. last bit-packer done) is reported, as the search time

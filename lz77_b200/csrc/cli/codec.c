@@ -11,8 +11,10 @@
  */
 #include "codec.h"
 
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "lz77_b200.h"
 
@@ -21,13 +23,14 @@ struct bitFILE {
     int mode;
 };
 
-static int g_device = 0, g_gpus = 1;
-static long g_piece_mib = 1024, g_out_mib = 4096;
+static int g_device = 0, g_gpus = 1, g_verbose = 0;
+static long g_piece_mib = 64, g_out_mib = 4096;
 
 void lz77_cli_set_device(int device) { g_device = device; }
 void lz77_cli_set_gpus(int n) { g_gpus = n < 1 ? 1 : n; }
 void lz77_cli_set_piece_mib(long mib) { g_piece_mib = mib < 1 ? 1 : mib; }
 void lz77_cli_set_out_mib(long mib) { g_out_mib = mib < 1 ? 1 : mib; }
+void lz77_cli_set_verbose(int on) { g_verbose = on; }
 
 struct bitFILE *bitIO_open(const char *path, int mode)
 {
@@ -136,81 +139,302 @@ static int put_bits(FILE *f, const unsigned char *src, long nbits, unsigned *acc
     return 0;
 }
 
+/*
+ * The reference's loop interleaves file I/O and compute a few KiB at a time
+ * (lz77.c:113-129 fread, bitio.c:80-93 fwrite).  Here whole pieces cross the library
+ * boundary, so the overlap is explicit: a ring of pinned piece buffers, a reader thread
+ * that fills them (fread), the calling thread that runs the GPU codec on the filled ones,
+ * and a writer thread that drains the results (fwrite) -- piece k+1 is being read and
+ * piece k-1 written while piece k is on the GPU.
+ */
+enum { RING = 3 };
+
+struct slot {
+    unsigned char *in, *out; /* pinned */
+    long n_in, n_out, cap;   /* bytes read / stream bytes produced (with its 4-byte header) / size of out */
+    int eof;                 /* last piece of the input */
+    int state;               /* 0 free, 1 filled, 2 encoded */
+};
+
+struct ring {
+    struct slot s[RING];
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    FILE *fin, *fout;
+    long piece;
+    int tbits, failed_read, failed_write, pieces_read_done;
+    unsigned acc;
+    int acc_bits, wrote_header;
+};
+
+static void ring_wait(struct ring *r, int i, int want)
+{
+    pthread_mutex_lock(&r->mu);
+    while (r->s[i].state != want)
+        pthread_cond_wait(&r->cv, &r->mu);
+    pthread_mutex_unlock(&r->mu);
+}
+
+static void ring_set(struct ring *r, int i, int state)
+{
+    pthread_mutex_lock(&r->mu);
+    r->s[i].state = state;
+    pthread_cond_broadcast(&r->cv);
+    pthread_mutex_unlock(&r->mu);
+}
+
+static void *reader_main(void *arg)
+{
+    struct ring *r = arg;
+    int i = 0, first = 1;
+    for (;;) {
+        struct slot *sl = &r->s[i];
+        ring_wait(r, i, 0);
+        sl->n_in = (long)fread(sl->in, 1, (size_t)r->piece, r->fin);
+        if (ferror(r->fin))
+            r->failed_read = 1;
+        sl->eof = sl->n_in < r->piece || r->failed_read;
+        if (sl->n_in == 0 && !first)
+            sl->eof = 2; /* nothing left: no piece, just the end */
+        first = 0;
+        ring_set(r, i, 1);
+        if (sl->eof)
+            return NULL;
+        i = (i + 1) % RING;
+    }
+}
+
+static void *writer_main(void *arg)
+{
+    struct ring *r = arg;
+    int i = 0;
+    for (;;) {
+        struct slot *sl = &r->s[i];
+        int eof;
+        ring_wait(r, i, 2);
+        eof = sl->eof;
+        if (sl->n_out > 0 && !r->failed_write) {
+            /* padding is < 8 < T bits, so the token count follows from the size */
+            long n_tokens = ((sl->n_out - 4) * 8) / r->tbits;
+            if (!r->wrote_header) { /* header, lz77.c:74-75 */
+                if (fwrite(sl->out, 1, 4, r->fout) != 4)
+                    r->failed_write = 1;
+                r->wrote_header = 1;
+            }
+            if (put_bits(r->fout, sl->out + 4, n_tokens * r->tbits, &r->acc, &r->acc_bits) != 0)
+                r->failed_write = 1;
+        }
+        ring_set(r, i, 0);
+        if (eof)
+            return NULL;
+        i = (i + 1) % RING;
+    }
+}
+
 void encode(FILE *file, struct bitFILE *out, int la, int sb)
 {
-    const long piece = piece_bytes();
     const int esb = sb == -1 ? LZ77_DEFAULT_SB : sb, ela = la == -1 ? LZ77_DEFAULT_LA : la;
-    const int tbits = lz77_token_bits(esb, ela);
-    long cap = 0;
-    unsigned char *in, *obuf = NULL;
-    unsigned acc = 0;
-    int acc_bits = 0, first = 1, rc;
+    struct ring r;
+    pthread_t reader, writer;
+    struct timespec t0, t1;
+    long cap, total_in = 0, total_out = 0;
+    int i, rc;
 
     bind_device();
-    in = lz77_gpu_host_alloc(piece);
-    if (in == NULL)
-        die("allocating the input buffer", LZ77_E_NOMEM);
-    for (;;) {
-        long n_out = 0, n_tokens;
-        long n_in = (long)fread(in, 1, (size_t)piece, file);
-        if (ferror(file)) {
+    memset(&r, 0, sizeof r);
+    r.piece = piece_bytes();
+    r.tbits = lz77_token_bits(esb, ela);
+    r.fin = file;
+    r.fout = out->file;
+    pthread_mutex_init(&r.mu, NULL);
+    pthread_cond_init(&r.cv, NULL);
+    /* small files: no point in pinning three full pieces */
+    {
+        long pos = ftell(file), size = -1;
+        if (pos >= 0 && fseek(file, 0, SEEK_END) == 0) {
+            size = ftell(file) - pos;
+            fseek(file, pos, SEEK_SET);
+        }
+        if (size >= 0 && size < r.piece) {
+            const long block = 1L << 19; /* a multiple of every block size */
+            r.piece = (size + block) / block * block;
+        }
+    }
+    /* the worst case is T/8 bytes per input byte; text and logs need well under one, so
+     * start there and fall back to the bound when a piece does not fit */
+    cap = r.piece + r.piece / 4 + 65536;
+    if (cap > lz77_gpu_encode_bound(r.piece, sb, la) + 16)
+        cap = lz77_gpu_encode_bound(r.piece, sb, la) + 16;
+    for (i = 0; i < RING; i++) {
+        r.s[i].in = lz77_gpu_host_alloc(r.piece);
+        r.s[i].out = lz77_gpu_host_alloc(cap);
+        r.s[i].cap = cap;
+        if (r.s[i].in == NULL || r.s[i].out == NULL)
+            die("allocating the piece buffers", LZ77_E_NOMEM);
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_create(&reader, NULL, reader_main, &r);
+    pthread_create(&writer, NULL, writer_main, &r);
+    for (i = 0;; i = (i + 1) % RING) {
+        struct slot *sl = &r.s[i];
+        int eof;
+        ring_wait(&r, i, 1);
+        eof = sl->eof;
+        sl->n_out = 0;
+        if (r.failed_read) {
             printf("Error loading the data in the window.\n"); /* lz77.c:79-82 */
-            break;
+        } else if (eof != 2) {
+            rc = codec_encode(sl->in, sl->n_in, sb, la, sl->out, sl->cap, &sl->n_out);
+            if (rc == LZ77_E_SPACE) { /* incompressible: this slot gets the worst-case buffer */
+                lz77_gpu_host_free(sl->out);
+                sl->cap = lz77_gpu_encode_bound(r.piece, sb, la) + 16;
+                sl->out = lz77_gpu_host_alloc(sl->cap);
+                if (sl->out == NULL)
+                    die("allocating the piece buffers", LZ77_E_NOMEM);
+                rc = codec_encode(sl->in, sl->n_in, sb, la, sl->out, sl->cap, &sl->n_out);
+            }
+            if (rc != LZ77_OK)
+                die("encoding", rc);
+            total_in += sl->n_in;
+            total_out += sl->n_out - 4;
         }
-        if (n_in == 0 && !first)
-            break;
-        if (obuf == NULL) {
-            cap = lz77_gpu_encode_bound(n_in < piece ? n_in : piece, sb, la) + 16;
-            obuf = lz77_gpu_host_alloc(cap);
-            if (obuf == NULL)
-                die("allocating the output buffer", LZ77_E_NOMEM);
-        }
-        rc = codec_encode(in, n_in, sb, la, obuf, cap, &n_out);
-        if (rc != LZ77_OK)
-            die("encoding", rc);
-        if (first && fwrite(obuf, 1, 4, out->file) != 4) /* header, lz77.c:74-75 */
-            perror("Writing output file");
-        /* padding is < 8 < T bits, so the token count follows from the size */
-        n_tokens = ((n_out - 4) * 8) / tbits;
-        if (put_bits(out->file, obuf + 4, n_tokens * tbits, &acc, &acc_bits) != 0)
-            perror("Writing output file");
-        first = 0;
-        if (n_in < piece)
+        ring_set(&r, i, 2);
+        if (eof)
             break;
     }
-    if (acc_bits > 0) /* zero padded last byte, bitio.c:180-182 */
-        fputc((int)(acc & 0xff), out->file);
-    lz77_gpu_host_free(in);
-    if (obuf != NULL)
-        lz77_gpu_host_free(obuf);
+    pthread_join(reader, NULL);
+    pthread_join(writer, NULL);
+    if (r.acc_bits > 0 && fputc((int)(r.acc & 0xff), out->file) == EOF) /* zero padded last byte, bitio.c:180-182 */
+        r.failed_write = 1;
+    if (fflush(out->file) != 0)
+        r.failed_write = 1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (g_verbose) {
+        double s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        fprintf(stderr, "lz77: encoded %ld -> %ld bytes in %.3f s (%.2f GB/s, read + GPU + write "
+                        "overlapped, %d GPU%s)\n",
+                total_in, total_out + 4, s, s > 0 ? (double)total_in / s / 1e9 : 0.0, g_gpus,
+                g_gpus > 1 ? "s" : "");
+    }
+    for (i = 0; i < RING; i++) {
+        lz77_gpu_host_free(r.s[i].in);
+        lz77_gpu_host_free(r.s[i].out);
+    }
+    pthread_mutex_destroy(&r.mu);
+    pthread_cond_destroy(&r.cv);
+    if (r.failed_write) { /* the reference swallows short writes (bitio.c:87-88); do not */
+        perror("Writing output file");
+        exit(EXIT_FAILURE);
+    }
 }
 
 /* copies nbits bits from bit src_bit of src to bit dst_bit of dst (LSB-first bit
- * numbering, bitio.c:203-298); the bits of dst behind the copy must be zero */
+ * numbering, bitio.c:203-298); the bits of dst behind the copy must be zero.  src must
+ * be readable for 8 bytes behind its last bit. */
 static void copy_bits(unsigned char *dst, long dst_bit, const unsigned char *src, long src_bit,
                       long nbits)
 {
-    if (((dst_bit | src_bit) & 7) == 0) {
+    if (((dst_bit ^ src_bit) & 7) == 0) {
+        /* same position inside the byte: up to 7 head bits, then whole bytes */
+        while (nbits > 0 && (dst_bit & 7) != 0) {
+            dst[dst_bit >> 3] |= (unsigned char)(((src[src_bit >> 3] >> (src_bit & 7)) & 1u) << (dst_bit & 7));
+            dst_bit++, src_bit++, nbits--;
+        }
         memcpy(dst + (dst_bit >> 3), src + (src_bit >> 3), (size_t)(nbits >> 3));
         dst_bit += nbits & ~7L;
         src_bit += nbits & ~7L;
         nbits &= 7;
+    } else {
+        /* bring dst to a byte boundary, then 8 destination bytes per step */
+        while (nbits > 0 && (dst_bit & 7) != 0) {
+            dst[dst_bit >> 3] |= (unsigned char)(((src[src_bit >> 3] >> (src_bit & 7)) & 1u) << (dst_bit & 7));
+            dst_bit++, src_bit++, nbits--;
+        }
+        while (nbits >= 64) {
+            const int sh = (int)(src_bit & 7); /* != 0 here */
+            unsigned long long lo, hi;
+            memcpy(&lo, src + (src_bit >> 3), 8);
+            hi = src[(src_bit >> 3) + 8];
+            lo = (lo >> sh) | (hi << (64 - sh));
+            memcpy(dst + (dst_bit >> 3), &lo, 8);
+            dst_bit += 64, src_bit += 64, nbits -= 64;
+        }
     }
-    while (nbits > 0) {
-        /* up to 8 bits that end at a source byte boundary */
-        int s_off = (int)(src_bit & 7), d_off = (int)(dst_bit & 7);
-        int take = 8 - s_off;
-        unsigned v;
-        if (take > nbits)
-            take = (int)nbits;
-        v = ((unsigned)src[src_bit >> 3] >> s_off) & ((1u << take) - 1u);
-        dst[dst_bit >> 3] |= (unsigned char)(v << d_off);
-        if (d_off + take > 8)
-            dst[(dst_bit >> 3) + 1] |= (unsigned char)(v >> (8 - d_off));
-        src_bit += take;
-        dst_bit += take;
-        nbits -= take;
+    while (nbits > 0) { /* the last < 64 bits */
+        dst[dst_bit >> 3] |= (unsigned char)(((src[src_bit >> 3] >> (src_bit & 7)) & 1u) << (dst_bit & 7));
+        dst_bit++, src_bit++, nbits--;
     }
+}
+
+/* n literal tokens (off 0, len 0, next = byte; lz77.c:249-251) from bit `bit` of dst on */
+static void put_literals(unsigned char *dst, long bit, const unsigned char *bytes, long n,
+                         int tbits, int lit_shift)
+{
+    long i;
+    if ((tbits & 7) == 0 && (bit & 7) == 0) {
+        unsigned char *p = dst + (bit >> 3) + (lit_shift >> 3); /* lit_shift = tbits - 8 */
+        const int step = tbits >> 3;
+        for (i = 0; i < n; i++, p += step)
+            *p = bytes[i];
+        return;
+    }
+    for (i = 0; i < n; i++) {
+        unsigned long long t = (unsigned long long)bytes[i] << lit_shift;
+        unsigned char v[8];
+        memcpy(v, &t, 8);
+        copy_bits(dst, bit, v, 0, tbits);
+        bit += tbits;
+    }
+}
+
+/* the writer side of decode(): one pending write at a time, on its own thread */
+struct wjob {
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    FILE *f;
+    const unsigned char *p;
+    long n;
+    int pending, quit, failed;
+};
+
+static void *wjob_main(void *arg)
+{
+    struct wjob *w = arg;
+    pthread_mutex_lock(&w->mu);
+    for (;;) {
+        while (!w->pending && !w->quit)
+            pthread_cond_wait(&w->cv, &w->mu);
+        if (!w->pending && w->quit)
+            break;
+        pthread_mutex_unlock(&w->mu);
+        if (w->n > 0 && fwrite(w->p, 1, (size_t)w->n, w->f) != (size_t)w->n)
+            w->failed = 1;
+        pthread_mutex_lock(&w->mu);
+        w->pending = 0;
+        pthread_cond_broadcast(&w->cv);
+    }
+    pthread_mutex_unlock(&w->mu);
+    return NULL;
+}
+
+static void wjob_wait(struct wjob *w)
+{
+    pthread_mutex_lock(&w->mu);
+    while (w->pending)
+        pthread_cond_wait(&w->cv, &w->mu);
+    pthread_mutex_unlock(&w->mu);
+}
+
+static void wjob_submit(struct wjob *w, const unsigned char *p, long n)
+{
+    pthread_mutex_lock(&w->mu);
+    while (w->pending)
+        pthread_cond_wait(&w->cv, &w->mu);
+    w->p = p;
+    w->n = n;
+    w->pending = 1;
+    pthread_cond_broadcast(&w->cv);
+    pthread_mutex_unlock(&w->mu);
 }
 
 /*
@@ -222,16 +446,20 @@ static void copy_bits(unsigned char *dst, long dst_bit, const unsigned char *src
  * output tail re-encoded as literal tokens (off 0, len 0, next = byte), then the
  * piece's tokens; the tail's bytes are dropped from the result.  The tail starts on a
  * block boundary of the output, so a stream of the block encoder stays aligned to
- * its blocks (and keeps decoding block-parallel).
+ * its blocks (and keeps decoding block-parallel).  The decoded piece is written by a
+ * second thread while the next piece is on the GPU (two output buffers).
  */
 void decode(struct bitFILE *file, FILE *out)
 {
     unsigned char hdr[4];
-    unsigned char *raw, *sbuf = NULL, *obuf = NULL, *hist;
-    long sbuf_cap = 0, obuf_cap = 0, hist_len = 0, raw_cap, piece_tokens;
-    long out_limit = g_out_mib << 20;
-    int sb, la, ob, lb, tbits, rc, last = 0;
+    unsigned char *raw, *sbuf = NULL, *obuf[2] = {NULL, NULL}, *hist;
+    long sbuf_cap = 0, obuf_cap[2] = {0, 0}, hist_len = 0, raw_cap, piece_tokens;
+    long out_limit = g_out_mib << 20, total_in = 4, total_out = 0;
+    int sb, la, ob, lb, tbits, rc, last = 0, cur = 0;
     long block;
+    struct wjob w;
+    pthread_t writer;
+    struct timespec t0, t1;
 
     bind_device();
     if (fread(hdr, 1, 4, file->file) != 4) {
@@ -248,14 +476,20 @@ void decode(struct bitFILE *file, FILE *out)
     tbits = ob + lb + 8;
     block = lz77_gpu_block_size(sb);
     /* whole tokens, a whole number of bytes */
-    piece_tokens = ((piece_bytes() / 4) * 8 / tbits) & ~7L;
+    piece_tokens = (piece_bytes() * 8 / tbits) & ~7L;
     if (piece_tokens < 8)
         piece_tokens = 8;
     raw_cap = piece_tokens / 8 * tbits;
-    raw = malloc((size_t)raw_cap + 8);
+    raw = malloc((size_t)raw_cap + 16);
     hist = malloc((size_t)(2 * block));
     if (raw == NULL || hist == NULL)
         die("allocating the input buffer", LZ77_E_NOMEM);
+    memset(&w, 0, sizeof w);
+    pthread_mutex_init(&w.mu, NULL);
+    pthread_cond_init(&w.cv, NULL);
+    w.f = out;
+    pthread_create(&writer, NULL, wjob_main, &w);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
 
     while (!last) {
         long got = (long)fread(raw, 1, (size_t)raw_cap, file->file);
@@ -264,13 +498,15 @@ void decode(struct bitFILE *file, FILE *out)
             perror("Error reading bits"); /* lz77.c:273-277 */
             exit(EXIT_FAILURE);
         }
+        memset(raw + got, 0, 16);
+        total_in += got;
         last = got < raw_cap;
         /* lz77.c:271-280: a short read ends the stream, trailing bits < T are padding */
         n_tok = last ? (got * 8) / tbits : piece_tokens;
         while (cursor < n_tok) {
-            long take = n_tok - cursor, n = 0, m = 0, need, bit, i;
+            long take = n_tok - cursor, m = 0, need, bit;
             for (;;) {
-                need = 4 + ((hist_len + take) * tbits + 7) / 8 + 16;
+                need = 4 + ((hist_len + take) * tbits + 7) / 8 + 32;
                 if (need > sbuf_cap) {
                     if (sbuf != NULL)
                         lz77_gpu_host_free(sbuf);
@@ -279,57 +515,85 @@ void decode(struct bitFILE *file, FILE *out)
                     if (sbuf == NULL)
                         die("allocating the input buffer", LZ77_E_NOMEM);
                 }
-                memset(sbuf, 0, (size_t)need);
+                /* header, the tail as literal tokens, the piece's tokens */
                 memcpy(sbuf, hdr, 4);
-                bit = 32;
-                for (i = 0; i < hist_len; i++) { /* the tail as literal tokens */
-                    unsigned char v[5];
-                    unsigned long long t = (unsigned long long)hist[i] << (ob + lb);
-                    v[0] = (unsigned char)t, v[1] = (unsigned char)(t >> 8);
-                    v[2] = (unsigned char)(t >> 16), v[3] = (unsigned char)(t >> 24);
-                    v[4] = (unsigned char)(t >> 32);
-                    copy_bits(sbuf, bit, v, 0, tbits);
-                    bit += tbits;
-                }
+                bit = 32 + hist_len * tbits;
+                if ((tbits & 7) != 0)
+                    memset(sbuf + 4, 0, (size_t)(need - 4));   /* bits are OR-ed in */
+                else
+                    memset(sbuf + 4, 0, (size_t)(hist_len * (tbits >> 3)));  /* literal tokens */
+                put_literals(sbuf, 32, hist, hist_len, tbits, ob + lb);
                 copy_bits(sbuf, bit, raw, cursor * tbits, take * tbits);
                 bit += take * tbits;
-                rc = lz77_gpu_decode_size(sbuf, (bit + 7) / 8, &n);
-                if (rc != LZ77_OK)
-                    die("decoding", rc);
-                if (n - hist_len <= out_limit || take <= 8)
+                if (obuf[cur] == NULL) {
+                    obuf_cap[cur] = (take * tbits / 8) * 3 + hist_len + (1L << 20);
+                    if (obuf_cap[cur] > out_limit + hist_len + 16)
+                        obuf_cap[cur] = out_limit + hist_len + 16;
+                    obuf[cur] = lz77_gpu_host_alloc(obuf_cap[cur]);
+                    if (obuf[cur] == NULL)
+                        die("allocating the output buffer", LZ77_E_NOMEM);
+                }
+                rc = codec_decode(sbuf, (bit + 7) / 8, obuf[cur], obuf_cap[cur] - 16, &m);
+                if (rc == LZ77_OK)
                     break;
-                take = (take / 2 + 7) & ~7L; /* highly compressible: smaller piece */
+                if (rc != LZ77_E_SPACE)
+                    die("decoding", rc);
+                /* m = the decoded size: a bigger buffer, or -- highly compressible input --
+                 * a smaller piece */
+                if (m - hist_len <= out_limit || take <= 8) {
+                    lz77_gpu_host_free(obuf[cur]);
+                    obuf_cap[cur] = m + m / 8 + 16;
+                    obuf[cur] = lz77_gpu_host_alloc(obuf_cap[cur]);
+                    if (obuf[cur] == NULL)
+                        die("allocating the output buffer", LZ77_E_NOMEM);
+                } else {
+                    take = (take / 2 + 7) & ~7L;
+                }
             }
-            if (n + 16 > obuf_cap) {
-                if (obuf != NULL)
-                    lz77_gpu_host_free(obuf);
-                obuf_cap = n + n / 4 + 16;
-                obuf = lz77_gpu_host_alloc(obuf_cap);
-                if (obuf == NULL)
-                    die("allocating the output buffer", LZ77_E_NOMEM);
-            }
-            rc = codec_decode(sbuf, (bit + 7) / 8, obuf, obuf_cap, &m);
-            if (rc != LZ77_OK)
-                die("decoding", rc);
-            if (m > hist_len &&
-                fwrite(obuf + hist_len, 1, (size_t)(m - hist_len), out) != (size_t)(m - hist_len))
-                perror("Writing output file");
             /* obuf starts on a block boundary of the output (or at its start): keep from
              * the last-but-one block boundary on, at least `block` > SB bytes */
             {
+                const long old_hist = hist_len;
                 long keep = (m % block) + block;
                 if (keep > m)
                     keep = m;
-                memcpy(hist, obuf + (m - keep), (size_t)keep);
+                memcpy(hist, obuf[cur] + (m - keep), (size_t)keep);
                 hist_len = keep;
+                wjob_submit(&w, obuf[cur] + old_hist, m - old_hist);
+                total_out += m - old_hist;
             }
+            cur ^= 1;
             cursor += take;
         }
+    }
+    wjob_wait(&w);
+    pthread_mutex_lock(&w.mu);
+    w.quit = 1;
+    pthread_cond_broadcast(&w.cv);
+    pthread_mutex_unlock(&w.mu);
+    pthread_join(writer, NULL);
+    if (fflush(out) != 0)
+        w.failed = 1;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (g_verbose) {
+        double s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+        fprintf(stderr, "lz77: decoded %ld -> %ld bytes in %.3f s (%.2f GB/s, read + GPU + write "
+                        "overlapped, %d GPU%s)\n",
+                total_in, total_out, s, s > 0 ? (double)total_out / s / 1e9 : 0.0, g_gpus,
+                g_gpus > 1 ? "s" : "");
     }
     free(raw);
     free(hist);
     if (sbuf != NULL)
         lz77_gpu_host_free(sbuf);
-    if (obuf != NULL)
-        lz77_gpu_host_free(obuf);
+    if (obuf[0] != NULL)
+        lz77_gpu_host_free(obuf[0]);
+    if (obuf[1] != NULL)
+        lz77_gpu_host_free(obuf[1]);
+    pthread_mutex_destroy(&w.mu);
+    pthread_cond_destroy(&w.cv);
+    if (w.failed) {
+        perror("Writing output file");
+        exit(EXIT_FAILURE);
+    }
 }

@@ -28,5 +28,6 @@ void lz77_cli_set_device(int device);
 void lz77_cli_set_gpus(int n);
 void lz77_cli_set_piece_mib(long mib);
 void lz77_cli_set_out_mib(long mib);
+void lz77_cli_set_verbose(int on); /* -v: bytes, seconds and GB/s on stderr */
 
 #endif

@@ -4,7 +4,7 @@
  * Same getopt string plus additive options that leave the file format alone: -g <device>,
  * -G <n> (encode / decode on the first n GPUs: runs of whole blocks per GPU, NCCL
  * scatter / gather inside liblz77b200.so), -p <MiB> (input bytes per library call) and
- * -m <MiB> (decoded bytes per library call).  Same limits
+ * -m <MiB> (decoded bytes per library call), -v (bytes, seconds, GB/s on stderr).  Same limits
  * (main.c:35-38), same messages and exit codes: every usage or open error
  * prints the reference's text on stderr and exits EXIT_FAILURE; -h prints the
  * usage and continues; the last of -c / -d wins; -d ignores -l / -s (the
@@ -41,7 +41,7 @@ int main(int argc, char *argv[])
     struct bitFILE *packed = NULL;
     int opt;
 
-    while ((opt = getopt(argc, argv, "cdi:o:l:s:hg:G:p:m:")) != -1) {
+    while ((opt = getopt(argc, argv, "cdi:o:l:s:hg:G:p:m:v")) != -1) {
         switch (opt) {
         case 'c':
             mode = MODE_ENCODE;
@@ -91,6 +91,9 @@ int main(int argc, char *argv[])
             break;
         case 'm':
             lz77_cli_set_out_mib(atol(optarg));
+            break;
+        case 'v':
+            lz77_cli_set_verbose(1);
             break;
         default:
             break;

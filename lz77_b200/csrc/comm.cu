@@ -477,7 +477,7 @@ int lz77_gpu_encode_sharded_device(const void *d_in, long n_in, int sb, int la, 
     if (n_tokens) *n_tokens = (long)k_total;
     memset(&c.last, 0, sizeof c.last);
     c.last.n_tokens = (long)K[rank];
-    c.last.launches = encode_launch_count(len);
+    c.last.launches = encode_launch_count(len, P);
     return LZ77_OK;
 }
 

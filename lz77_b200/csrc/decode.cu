@@ -178,6 +178,139 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
     }
 }
 
+// The same pass for byte-aligned tokens (T = 24: the default parameters; T = 32: -s 65535
+// -l 255), an order of magnitude fewer instructions: a thread owns 16 CONSECUTIVE tokens, so
+// the running position inside its run is 16 additions in registers and the CTA needs one
+// warp scan instead of one per row of 32 tokens.  The CTA's 4096 tokens are fetched with
+// coalesced 32-bit loads (the stream is word aligned at every 4096th token) into shared
+// memory, from where each thread reads its 48 or 64 bytes with 128-bit loads (thread
+// stride 48 bytes, or 80 with padding: conflict-free per quarter warp).  The per-token
+// work left -- tile table, block-containment check -- only runs in the few threads whose
+// run touches a tile boundary or the first `window` bytes of a block.
+template <int kT>
+__global__ void __launch_bounds__(kDsThreads)
+lz77_decode_scan_fast_kernel(const uint32_t *__restrict__ words, long long n_words,
+                             long long n_tokens, Params P, int tile_shift,
+                             unsigned long long *status, long long *__restrict__ tile_tok,
+                             long long *__restrict__ tile_pos, uint32_t *__restrict__ group_pos,
+                             unsigned int *tickets, DecodeInfo *info)
+{
+    constexpr int kPer = kDsRows;                    // consecutive tokens per thread
+    constexpr int kTw = kPer * kT / 32;              // words per thread: 12 or 16
+    constexpr int kStride = kT == 32 ? 20 : 12;      // words between two threads' runs
+    __shared__ __align__(16) uint32_t s_tok[kDsThreads * kStride];
+    __shared__ long long s_chunk;
+    __shared__ unsigned long long s_warp_tot[kDsThreads / 32];
+    __shared__ unsigned long long s_prefix;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_chunk = atomicAdd(&tickets[0], 1u);  // chunks start in order
+    __syncthreads();
+    const long long c = s_chunk;
+    const long long tok0 = c * kDsChunk;
+    const long long w0 = 1 + tok0 * kT / 32;  // (4096 tokens are a whole number of words)
+    for (int i = threadIdx.x; i < kDsThreads * kTw; i += kDsThreads) {
+        const long long w = w0 + i;
+        const uint32_t v = w < n_words ? __ldg(words + w) : 0u;
+        s_tok[(i / kTw) * kStride + (i % kTw)] = v;
+    }
+    __syncthreads();
+
+    uint32_t wv[kTw + 1];
+    {
+        const uint4 *p = reinterpret_cast<const uint4 *>(s_tok + threadIdx.x * kStride);
+#pragma unroll
+        for (int q = 0; q < kTw / 4; q++) {
+            const uint4 v = p[q];
+            wv[4 * q] = v.x, wv[4 * q + 1] = v.y, wv[4 * q + 2] = v.z, wv[4 * q + 3] = v.w;
+        }
+        wv[kTw] = 0u;
+    }
+    const uint32_t len_mask = (1u << P.lb) - 1u, off_mask = (1u << P.ob) - 1u;
+    const long long k_first = tok0 + (long long)threadIdx.x * kPer;
+    uint32_t tok[kPer];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        if (kT == 32) {
+            tok[i] = wv[i];
+        } else {
+            const int b = 3 * i;
+            tok[i] = __funnelshift_r(wv[b >> 2], wv[(b >> 2) + 1], (b & 3) * 8) & 0xffffffu;
+        }
+        if (k_first + i < n_tokens) sum += ((tok[i] >> P.ob) & len_mask) + 1u;
+    }
+    // exclusive prefix of the thread sums inside the CTA
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = inc;
+    __syncthreads();
+    unsigned long long warp_off = 0, chunk_total = 0;
+#pragma unroll
+    for (int w = 0; w < kDsThreads / 32; w++) {
+        const unsigned long long t = s_warp_tot[w];
+        if (w < warp) warp_off += t;
+        chunk_total += t;
+    }
+    // decoupled look-back: warp 0 resolves this chunk's exclusive prefix
+    if (warp == 0) {
+        unsigned long long exclusive = 0;
+        if (c > 0) {
+            if (lane == 0) atomicExch(&status[c], kFlagAgg | chunk_total);
+            long long idx = c - 1 - lane;
+            while (true) {
+                unsigned long long sv = idx >= 0 ? ld_volatile_u64(&status[idx]) : kFlagInc;
+                while (__any_sync(0xffffffffu, (sv >> 62) == 0)) {
+                    if ((sv >> 62) == 0) sv = ld_volatile_u64(&status[idx]);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                const unsigned long long val = sv & kValMask;
+                if (inc_mask) {
+                    const int first = __ffs(inc_mask) - 1;
+                    exclusive += warp_sum_u64(lane <= first ? val : 0ull);
+                    break;
+                }
+                exclusive += warp_sum_u64(val);
+                idx -= 32;
+            }
+        }
+        if (lane == 0) {
+            atomicExch(&status[c], kFlagInc | (exclusive + chunk_total));
+            s_prefix = exclusive;
+        }
+    }
+    __syncthreads();
+    if (k_first >= n_tokens) return;
+    const long long p_first = (long long)(s_prefix + warp_off + (unsigned long long)(inc - sum));
+    const long long p_end = p_first + (long long)sum;
+    if ((threadIdx.x & 1) == 0) group_pos[k_first >> 5] = (uint32_t)p_first;
+    if (k_first + kPer >= n_tokens) info->n_out = (unsigned long long)p_end;  // holds the last token
+
+    const long long tile_bytes = 1LL << tile_shift;
+    const bool tile_edge = (((p_first + tile_bytes - 1) >> tile_shift) << tile_shift) < p_end;
+    const long long q0 = p_first & (P.block - 1);
+    const bool near_block_start = q0 < (long long)P.window || q0 + (long long)sum > P.block;
+    if (!tile_edge && !near_block_start) return;
+    long long pos = p_first;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        if (k_first + i >= n_tokens) break;
+        const uint32_t len = (tok[i] >> P.ob) & len_mask;
+        const long long Lr = (long long)len + 1;
+        if (len > 0 && (long long)(tok[i] & off_mask) > (pos & (P.block - 1))) info->cross_block = 1u;
+        const long long j = (pos + tile_bytes - 1) >> tile_shift;
+        if ((j << tile_shift) < pos + Lr) {
+            tile_tok[j] = k_first + i;
+            tile_pos[j] = pos;
+        }
+        pos += Lr;
+    }
+}
+
 // The chunked host path reads the scan's progress without a D2H memcpy: the output
 // position behind the last scanned token, bit 63 = a match left its block.
 __global__ void lz77_decode_publish_kernel(const DecodeInfo *info,
@@ -269,6 +402,12 @@ __global__ void lz77_token_at_kernel(const uint32_t *__restrict__ words, long lo
 #endif
 #ifndef LZ77_DEC_THREADS
 #define LZ77_DEC_THREADS 512
+#endif
+#ifndef LZ77_DEC_WORDCOPY
+#define LZ77_DEC_WORDCOPY 1  // matches of <= 16 bytes that do not overlap: word loads, byte stores
+#endif
+#ifndef LZ77_DEC_EAGER
+#define LZ77_DEC_EAGER 0  // 1: copy whatever is ready at once instead of waiting for the set to settle
 #endif
 constexpr int kDecThreadsSmall = LZ77_DEC_THREADS;  // CTA size for 64 KiB tiles (3 CTAs/SM)
 constexpr int kDecSpins = LZ77_DEC_SPINS;        // polls without progress before backing off
@@ -474,7 +613,7 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                 const unsigned rm = __ballot_sync(0xffffffffu, ready);
                 // copy in as few divergent passes as possible: when every pending
                 // lane is ready, or when the ready set stopped growing
-                const bool go = rm != 0u && (rm == um || rm == prev_rm);
+                const bool go = rm != 0u && (LZ77_DEC_EAGER || rm == um || rm == prev_rm);
                 prev_rm = rm;
                 if (go) {
                     if (ready) {  // ascending byte copy, lz77.c:178-188
@@ -482,7 +621,20 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                         if (fast) {
                             const volatile uint8_t *src = tile + s_rel;
                             uint8_t *dst = tile + pos_rel;
-                            if (off >= len) {
+                            if (LZ77_DEC_WORDCOPY && off >= len && len <= 16) {
+                                // source and destination do not overlap, at most 16 bytes:
+                                // five aligned words up front (one round of loads instead of
+                                // a load per byte), then predicated byte stores
+                                const volatile uint32_t *sw =
+                                    reinterpret_cast<const volatile uint32_t *>(tile + (s_rel & ~3));
+                                const int sh = (s_rel & 3) * 8;
+                                const uint32_t a0 = sw[0], a1 = sw[1], a2 = sw[2], a3 = sw[3], a4 = sw[4];
+                                const uint32_t v[4] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh),
+                                                       __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh)};
+#pragma unroll
+                                for (int i = 0; i < 16; i++)
+                                    if (i < len) dst[i] = (uint8_t)(v[i >> 2] >> ((i & 3) * 8));
+                            } else if (off >= len) {
                                 for (int i = 0; i < len; i++) dst[i] = src[i];
                             } else {
                                 int r = 0;
@@ -605,10 +757,14 @@ cudaError_t launch_decode_scan_range(const uint32_t *d_in_words, long long n_in_
     }
     const long long n_chunks = (tok_end - tok_begin + kDsChunk - 1) / kDsChunk;
     const long long n_words = (n_in_bytes + 3) / 4;
-    if (n_chunks > 0)
-        lz77_decode_scan_kernel<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(
-            d_in_words, n_words, tok_end, P, P.tile_shift, s.status, s.tile_tok, s.tile_pos,
-            s.group_pos, s.tickets, s.info);
+    if (n_chunks > 0) {
+        auto kern = P.tbits == 24   ? lz77_decode_scan_fast_kernel<24>
+                    : P.tbits == 32 ? lz77_decode_scan_fast_kernel<32>
+                                    : lz77_decode_scan_kernel;  // any other width
+        kern<<<(unsigned)n_chunks, kDsThreads, 0, st>>>(d_in_words, n_words, tok_end, P,
+                                                        P.tile_shift, s.status, s.tile_tok,
+                                                        s.tile_pos, s.group_pos, s.tickets, s.info);
+    }
     if (host_n_out) lz77_decode_publish_kernel<<<1, 1, 0, st>>>(s.info, host_n_out);
     return cudaGetLastError();
 }

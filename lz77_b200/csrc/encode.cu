@@ -223,6 +223,8 @@ lz77_pack_kernel(const uint32_t *__restrict__ tok_tmp, const uint32_t *__restric
 
 size_t encode_scratch_bytes(long long n_in, const Params &P)
 {
+    if (parse_bucket_fused(P))  // no unpacked tokens in HBM: look-back words + a spill area
+        return 4096 + parse_bucket_fused_scratch(n_in);
     const long long n_seg = (n_in + kSegBytes - 1) / kSegBytes;
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
     size_t b = 0;
@@ -249,6 +251,16 @@ EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P)
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
     char *p = (char *)scratch;
     EncodePlan pl;
+    pl.n_total = n_in_total;
+    pl.fused = nullptr;
+    if (parse_bucket_fused(P)) {
+        pl.tok_tmp = pl.seg_ntok = nullptr;
+        pl.prefix = pl.partial = nullptr;
+        pl.total = (unsigned long long *)p;
+        pl.fused = p + 256;
+        pl.big = nullptr;
+        return pl;
+    }
     pl.tok_tmp = (uint32_t *)carve(p, (size_t)(n_seg * kSegBytes) * sizeof(uint32_t));
     pl.seg_ntok = (uint32_t *)carve(p, (size_t)n_seg * sizeof(uint32_t));
     pl.prefix = (unsigned long long *)carve(p, (size_t)n_seg * sizeof(unsigned long long));
@@ -272,10 +284,24 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long pre_base, lo
                                 long long n_chunk, bool first, const Params &P,
                                 const EncodePlan &pl,
                                 uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
-                                int phase, unsigned long long *host_total)
+                                int phase, unsigned long long *host_total, int slot)
 {
     const uint8_t *d_in = d_in_base + lo;
     const long long pre = P.history ? pre_base + lo : 0;  // the earlier chunks are history
+    if (pl.fused) {
+        // 24-bit tokens, small window: search, parse and pack are one kernel (phase 1)
+        if (phase == 2) return cudaSuccess;
+        if (ev) cudaEventRecord(ev->e[0], st);
+        cudaError_t rc = launch_parse_bucket_fused(d_in_base, lo, n_chunk, pl.n_total, pre, first,
+                                                   slot, P, pl.fused, (uint8_t *)d_out_words,
+                                                   pl.total, host_total, st);
+        if (ev) {
+            cudaEventRecord(ev->e[1], st);
+            cudaEventRecord(ev->e[2], st);
+            cudaEventRecord(ev->e[3], st);
+        }
+        return rc;
+    }
     const long long seg0 = lo / kSegBytes;
     const long long n_seg = (n_chunk + kSegBytes - 1) / kSegBytes;
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
@@ -328,12 +354,13 @@ cudaError_t launch_encode(const uint8_t *d_in, long long n_in, long long pre, co
 {
     const EncodePlan pl = encode_plan(scratch, n_in, P);
     *d_total_tokens = pl.total;
-    return launch_encode_chunk(d_in, pre, 0, n_in, true, P, pl, d_out_words, st, ev, 0, nullptr);
+    return launch_encode_chunk(d_in, pre, 0, n_in, true, P, pl, d_out_words, st, ev, 0, nullptr, 0);
 }
 
-int encode_launch_count(long long n_in)
+int encode_launch_count(long long n_in, const Params &P)
 {
     if (n_in <= 0) return 1;
+    if (parse_bucket_fused(P)) return 1;  // search + parse + pack in one kernel
     return 6;  // parse, 3 x scan, pack-prepare, pack
 }
 

@@ -11,7 +11,7 @@ struct StageEvents {
 
 // ---- encoder (encode.cu) ---------------------------------------------------
 size_t encode_scratch_bytes(long long n_in, const Params &P);
-int encode_launch_count(long long n_in);
+int encode_launch_count(long long n_in, const Params &P);
 // d_out_words must hold 4 + ceil(n_in * T / 8) bytes rounded up to 16.
 // *d_total_tokens receives a device pointer (inside scratch) to the token count.
 // `pre`: valid input bytes in front of d_in (history mode only; 0 otherwise)
@@ -27,6 +27,8 @@ struct EncodePlan {
     unsigned long long *partial;
     unsigned long long *total;  // running token count (device)
     void *big;                  // large-window bucket tables (search_bigwin.cu)
+    void *fused;                // fused search + pack path: look-back words, tickets, spill
+    long long n_total;          // input bytes of the whole call
 };
 EncodePlan encode_plan(void *scratch, long long n_in_total, const Params &P);
 long long encode_chunk_granule();
@@ -34,13 +36,24 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long pre_base, lo
                                 long long n_chunk, bool first, const Params &P,
                                 const EncodePlan &pl,
                                 uint32_t *d_out_words, cudaStream_t st, StageEvents *ev,
-                                int phase, unsigned long long *host_total);
+                                int phase, unsigned long long *host_total, int slot);
 
 // bucketed longest-match search + greedy parse (search_bucket.cu)
 // `pre`: valid input bytes in front of d_in (history mode reaches back into them)
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long pre,
                                 const Params &P, uint32_t *tok_tmp, uint32_t *seg_ntok,
                                 cudaStream_t st);
+
+// 24-bit tokens and a window <= 8191: search + parse + pack in one persistent kernel
+// (search_bucket.cu); `slot` < 64 names the ticket of this launch (launches of one call
+// that may run side by side need different ones)
+bool parse_bucket_fused(const Params &P);
+size_t parse_bucket_fused_scratch(long long n_total);
+cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long long n_in,
+                                      long long n_total, long long pre, bool first, int slot,
+                                      const Params &P, void *scratch, uint8_t *d_out,
+                                      unsigned long long *total, unsigned long long *host_total,
+                                      cudaStream_t st);
 
 // large windows: block-level buckets (search_bigwin.cu)
 size_t bigwin_scratch_bytes(long long n_in, const Params &P);

@@ -22,6 +22,19 @@
 //     A match of length 1 can sit in many buckets; when nothing longer exists the
 //     warp scans the staged window forward (SWAR byte compare, 512 bytes per
 //     step) for the oldest occurrence of the first byte.
+//   emit (fused path, 24-bit tokens: the default parameters)
+//     replaces writecode() lz77.c:246-252 + bitIO_write() bitio.c:203-239 inside the
+//     search kernel.  A warp keeps its segment's tokens in shared memory (the counter
+//     area of the build, dead by then; tokens beyond 512 per segment -- incompressible
+//     data -- spill to a small per-CTA area in global memory).  When the tile is parsed
+//     its token count enters a decoupled look-back over the tiles (tiles are handed out
+//     by ticket, so every predecessor is running or done), which yields the tile's place
+//     in the stream; the CTA packs its tokens to 3 bytes each in shared memory -- at the
+//     same offset modulo 16 as their place in the stream -- and writes them with 128-bit
+//     stores, single bytes at the two ends (T is a multiple of 8: no tile shares a byte
+//     with its neighbour, so nothing has to be zeroed or merged).  No token ever
+//     travels through HBM unpacked.  Other token widths keep the generic path: 32-bit
+//     tokens to scratch, count scan, lz77_pack_kernel (encode.cu).
 #include "kernels.cuh"
 #include "match.cuh"
 
@@ -189,23 +202,44 @@ __device__ __forceinline__ int group_lower_bound_s(uint32_t se, int n, int lo, i
 }
 
 // kLanes lanes (a "group": 32, 16 or 8) cooperate on one parse segment, so a warp
-// parses 32 / kLanes segments side by side: the per-token scalar work (target
-// load, bucket lookup, window bound, reduction, emit) is issued once for all
-// the groups of a warp that are in step.
+// parses 32 / kLanes segments side by side.  (Measured: groups of 16 or 8 lanes with
+// 512- or 256-byte segments -- the same 8 KiB tile -- are no faster than one warp per
+// 1 KiB segment: the groups of a warp do not stay in step.  The fused path is written
+// for kLanes == 32.)
 #ifndef LZ77_PARSE_MINBLOCKS
 #define LZ77_PARSE_MINBLOCKS 1
 #endif
-template <bool kSmallLA, int kWarps, int kLanes, typename PosT, bool kSortedGlobal>
-__global__ void __launch_bounds__(kWarps * 32, LZ77_PARSE_MINBLOCKS)
+
+constexpr int kTokBuf = 512;                     // tokens per segment kept in shared memory
+constexpr int kTokSpill = kSegBytes - kTokBuf;   // the rest of a worst-case segment: global
+constexpr unsigned long long kLbAgg = 1ull << 62, kLbInc = 2ull << 62, kLbVal = (1ull << 62) - 1;
+
+struct FusedEmit {                 // outputs of the fused path (kFused)
+    uint8_t *out;                  // the stream (header + tokens), 16-byte aligned
+    unsigned long long *status;    // look-back state, one word per tile of the whole call
+    unsigned int *ticket;          // tile ticket of this launch
+    unsigned long long *total;     // tokens up to and including this launch
+    unsigned long long *host_total;  // the same in mapped pinned memory (may be null)
+    uint32_t *spill;               // gridDim.x * kWarps * kTokSpill tokens
+    long long tile0;               // index of this launch's first tile in the whole call
+    int write_header;
+};
+
+template <bool kSmallLA, int kWarps, int kLanes, typename PosT, bool kSortedGlobal, bool kFused>
+__global__ void __launch_bounds__(kWarps * 32, kFused ? 4 : LZ77_PARSE_MINBLOCKS)
 lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long pre, Params P,
                          int hist_cap, long long n_tiles, uint32_t *__restrict__ tok_tmp,
                          uint32_t *__restrict__ seg_ntok, PosT *sorted_global,
-                         long long sorted_stride)
+                         long long sorted_stride, FusedEmit F)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_total;
+    __shared__ long long s_tile;                 // fused: the tile this CTA drew
+    __shared__ int s_cnt[kWarps];                // fused: tokens per segment of the tile
+    __shared__ unsigned long long s_excl;        // fused: tokens in front of the tile
+    static_assert(!kFused || kLanes == 32, "the fused emit is written for one warp per segment");
 
     constexpr int kThreads = kWarps * 32;
     constexpr int kSegsPerWarp = 32 / kLanes;
@@ -237,7 +271,20 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
     __syncthreads();
 
     uint32_t phase = 0;
-    for (long long tile_i = blockIdx.x; tile_i < n_tiles; tile_i += gridDim.x, phase ^= 1u) {
+    for (long long tile_i = blockIdx.x;; tile_i += gridDim.x, phase ^= 1u) {
+        if (kFused) {
+            // tiles are handed out in order: whoever looks back at a tile finds it running
+            if (threadIdx.x == 0) {
+                const unsigned int t = atomicAdd(F.ticket, 1u);
+                // every CTA draws until it is turned away: the last draw of the launch
+                // leaves the ticket at zero for the next launch that uses this slot
+                if ((long long)t == n_tiles + (long long)gridDim.x - 1) atomicExch(F.ticket, 0u);
+                s_tile = (long long)t;
+            }
+            __syncthreads();
+            tile_i = s_tile;
+        }
+        if (tile_i >= n_tiles) break;
         const long long tile_lo = tile_i * tile_bytes;
         // the window starts at the block (independent blocks) or, in history mode, reaches
         // back across block seams into the `pre` valid bytes in front of `in`
@@ -359,10 +406,16 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
             const int seg_end = (int)(seg_hi - src_lo) + dst0;
             int p0 = (int)(seg_lo - src_lo) + dst0;
             const int first_idx = dst0 + hist_al - (int)hist;  // oldest byte a match may start at
-            uint32_t *tok_row = tok_tmp + sgm * kSegBytes;
+            uint32_t *tok_row = kFused ? nullptr : tok_tmp + sgm * kSegBytes;
             const int len_shift = P.ob, lit_shift = P.ob + P.lb;
             const int la = P.la, window = P.window;
             uint32_t *tok_at = tok_row;  // a running pointer: no address arithmetic per token
+            // fused: the segment's tokens stay in shared memory (the counters of the build)
+            uint32_t tok_sa = smem_u32(cnt) + (uint32_t)warp * (kTokBuf * 4u);
+            const uint32_t tok_sa_end = tok_sa + kTokBuf * 4u;
+            uint32_t *spill_at = kFused ? F.spill + ((size_t)blockIdx.x * kWarps + warp) * kTokSpill
+                                        : nullptr;
+            int ntok_f = 0;
 
             while (p0 < seg_end) {
                 const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
@@ -469,14 +522,119 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                 // one 4-byte store per token by one lane: fewer instructions than
                 // collecting rows of 32 tokens in registers (measured 9.6 -> 9.4 ms), and
                 // L2 merges the sectors
-                if (sl == 0) *tok_at = tok;
-                tok_at++;
+                if (kFused) {
+                    if (tok_sa < tok_sa_end) {
+                        if (sl == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(tok_sa), "r"(tok));
+                        tok_sa += 4u;
+                    } else {
+                        if (sl == 0) *spill_at = tok;
+                        spill_at++;
+                    }
+                    ntok_f++;
+                } else {
+                    if (sl == 0) *tok_at = tok;
+                    tok_at++;
+                }
                 p0 += len + 1;
             }
-            const int ntok = (int)(tok_at - tok_row);
-            if (sl == 0) seg_ntok[sgm] = (uint32_t)ntok;
+            if (kFused) {
+                if (lane == 0) s_cnt[warp] = ntok_f;
+            } else {
+                const int ntok = (int)(tok_at - tok_row);
+                if (sl == 0) seg_ntok[sgm] = (uint32_t)ntok;
+            }
+        } else if (kFused) {
+            if (lane == 0) s_cnt[warp] = 0;
         }
         __syncthreads();  // the next tile overwrites the staged data and the buckets
+
+        if (kFused) {
+            // ---- the tile's place in the stream: decoupled look-back over the tiles ----
+            int pre_w = 0, k_tile = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) {
+                const int c = s_cnt[w];
+                if (w < warp) pre_w += c;
+                k_tile += c;
+            }
+            const long long gt = F.tile0 + tile_i;  // index in the whole call
+            if (warp == 0) {
+                unsigned long long excl = 0;
+                if (gt > 0) {
+                    if (lane == 0) atomicExch(&F.status[gt], kLbAgg | (unsigned long long)k_tile);
+                    long long idx = gt - 1 - lane;
+                    while (true) {
+                        unsigned long long sv = kLbInc;  // in front of the first tile: nothing
+                        if (idx >= 0)
+                            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(sv) : "l"(F.status + idx) : "memory");
+                        while (__any_sync(0xffffffffu, (sv >> 62) == 0)) {
+                            if ((sv >> 62) == 0) {
+                                __nanosleep(64);
+                                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(sv) : "l"(F.status + idx) : "memory");
+                            }
+                        }
+                        const unsigned inc_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                        unsigned long long v = sv & kLbVal;
+                        if (inc_mask) {
+                            const int first = __ffs(inc_mask) - 1;
+                            v = lane <= first ? v : 0ull;
+                        }
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                        excl += v;
+                        if (inc_mask) break;
+                        idx -= 32;
+                    }
+                }
+                if (lane == 0) {
+                    const unsigned long long incl = excl + (unsigned long long)k_tile;
+                    if (tile_i == n_tiles - 1) {  // the launch's last tile: the running total
+                        *F.total = incl;
+                        if (F.host_total) {
+                            *reinterpret_cast<volatile unsigned long long *>(F.host_total) = incl;
+                            __threadfence_system();
+                        }
+                        __threadfence();
+                    }
+                    atomicExch(&F.status[gt], kLbInc | incl);
+                    s_excl = excl;
+                }
+            }
+            __syncthreads();
+            // ---- pack: 3 bytes per token, at the stream's offset modulo 16 ----
+            const unsigned long long g0 = 4ull + 3ull * s_excl;  // byte offset in the stream
+            const int shift = (int)(g0 & 15ull);
+            uint8_t *pk = reinterpret_cast<uint8_t *>(sorted);   // the bucket lists are dead now
+            {
+                const uint32_t *buf = cnt + warp * kTokBuf;
+                const uint32_t *sp = F.spill + ((size_t)blockIdx.x * kWarps + warp) * kTokSpill;
+                const int mine = s_cnt[warp];
+                for (int t = lane; t < mine; t += 32) {
+                    const uint32_t tok = t < kTokBuf ? buf[t] : sp[t - kTokBuf];
+                    uint8_t *b = pk + shift + 3 * (pre_w + t);
+                    b[0] = (uint8_t)tok;
+                    b[1] = (uint8_t)(tok >> 8);
+                    b[2] = (uint8_t)(tok >> 16);
+                }
+            }
+            __syncthreads();
+            // ---- write: 128-bit stores, single bytes at the two ends ----
+            {
+                uint8_t *dstb = F.out + (g0 - (unsigned long long)shift);  // 16-byte aligned
+                const int end = shift + 3 * k_tile;
+                const int c_lo = shift == 0 ? 0 : 16;
+                const int c_hi = end & ~15;
+                for (int c = c_lo + 16 * (int)threadIdx.x; c < c_hi; c += 16 * kThreads)
+                    *reinterpret_cast<uint4 *>(dstb + c) = *reinterpret_cast<const uint4 *>(pk + c);
+                for (int i = shift + (int)threadIdx.x; i < min(c_lo, end); i += kThreads)
+                    dstb[i] = pk[i];
+                for (int i = max(c_hi, c_lo) + (int)threadIdx.x; i < end; i += kThreads)
+                    dstb[i] = pk[i];
+                if (gt == 0 && F.write_header && threadIdx.x == 0)
+                    *reinterpret_cast<uint32_t *>(F.out) = (uint32_t)P.sb | ((uint32_t)P.la << 16);
+            }
+            // (the ticket's barrier at the top of the loop keeps the next tile off this one)
+        }
     }
 }
 
@@ -488,6 +646,21 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
 #ifndef LZ77_PARSE_LANES
 #define LZ77_PARSE_LANES 32
 #endif
+
+bool parse_bucket_fused(const Params &P) { return P.tbits == 24 && P.window <= 8191; }
+
+// scratch of the fused path for a call over n_total input bytes: look-back words of all
+// its tiles, the tickets (one per launch that may be in flight), the spill area of one
+// resident grid
+constexpr int kMaxTickets = 64;
+constexpr int kFusedGridMax = 148 * 4 * 2;
+size_t parse_bucket_fused_scratch(long long n_total)
+{
+    const long long tile_bytes = (long long)LZ77_PARSE_WARPS * kSegBytes;
+    const long long n_tiles = (n_total + tile_bytes - 1) / tile_bytes;
+    return (size_t)(n_tiles + 64) * 8 + (size_t)kMaxTickets * 4 + 256 +
+           (size_t)kFusedGridMax * LZ77_PARSE_WARPS * kTokSpill * 4 + 1024;
+}
 
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long pre,
                                 const Params &P, uint32_t *tok_tmp, uint32_t *seg_ntok,
@@ -504,13 +677,87 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long p
     smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // bucket starts
     smem += (size_t)kBuckets * (kW / 2) * 4;                   // per-warp counters
     smem += data_cap * sizeof(uint16_t) + 80;                  // sorted positions + one round of padding
-    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, kL, uint16_t, false>
-                         : lz77_parse_bucket_kernel<false, kW, kL, uint16_t, false>;
+    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, kL, uint16_t, false, false>
+                         : lz77_parse_bucket_kernel<false, kW, kL, uint16_t, false, false>;
     cudaError_t rc =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     kern<<<(unsigned)n_tiles, kW * 32, smem, st>>>(d_in, n_in, pre, P, hist_cap, n_tiles, tok_tmp,
-                                                   seg_ntok, (uint16_t *)nullptr, 0);
+                                                   seg_ntok, (uint16_t *)nullptr, 0, FusedEmit{});
+    return cudaGetLastError();
+}
+
+// The fused path: search + parse + pack in one persistent kernel.  `scratch` as sized by
+// parse_bucket_fused_scratch() for the whole call; `first` zeroes the look-back state
+// (every later chunk of the call continues behind it); slot = the ticket of this launch.
+cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long long n_in,
+                                      long long n_total, long long pre, bool first, int slot,
+                                      const Params &P, void *scratch, uint8_t *d_out,
+                                      unsigned long long *total, unsigned long long *host_total,
+                                      cudaStream_t st)
+{
+    constexpr int kW = LZ77_PARSE_WARPS;
+    const bool small_la = P.la <= 16;
+    const int hist_cap = (P.window + 15) & ~15;
+    const long long tile_bytes = (long long)kW * kSegBytes;
+    const long long n_tiles_total = (n_total + tile_bytes - 1) / tile_bytes;
+    const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
+    char *p = (char *)scratch;
+    unsigned long long *status = (unsigned long long *)p;
+    p += (size_t)(n_tiles_total + 64) * 8;
+    unsigned int *tickets = (unsigned int *)p;
+    p += (size_t)kMaxTickets * 4 + 256;
+    uint32_t *spill = (uint32_t *)p;
+    cudaError_t rc;
+    if (first) {
+        rc = cudaMemsetAsync(scratch, 0, (size_t)(n_tiles_total + 64) * 8 + (size_t)kMaxTickets * 4, st);
+        if (rc != cudaSuccess) return rc;
+    }
+    if (slot < 0 || slot >= kMaxTickets) return cudaErrorInvalidValue;
+    if (n_tiles == 0) {  // empty input: the header alone
+        if (first) {
+            const uint32_t hdr = (uint32_t)P.sb | ((uint32_t)P.la << 16);
+            rc = cudaMemcpyAsync(d_out, &hdr, 4, cudaMemcpyHostToDevice, st);
+            if (rc != cudaSuccess) return rc;
+            rc = cudaMemsetAsync(total, 0, 8, st);
+            if (rc != cudaSuccess) return rc;
+        }
+        return cudaSuccess;
+    }
+    const size_t data_cap = (size_t)hist_cap + (size_t)tile_bytes + 64;
+    size_t smem = (data_cap + 15) & ~(size_t)15;
+    smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;
+    smem += (size_t)kBuckets * (kW / 2) * 4;   // counters, then the tokens of the 8 segments
+    static_assert((size_t)kBuckets * (LZ77_PARSE_WARPS / 2) * 4 >= (size_t)LZ77_PARSE_WARPS * kTokBuf * 4,
+                  "the token buffers live in the counter area");
+    // sorted positions, then the tile's packed tokens (worst case one token per byte)
+    size_t tail = data_cap * sizeof(uint16_t) + 80;
+    const size_t pk_need = (size_t)tile_bytes * 3 + 32;
+    if (tail < pk_need) tail = pk_need;
+    smem += tail;
+    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, 32, uint16_t, false, true>
+                         : lz77_parse_bucket_kernel<false, kW, 32, uint16_t, false, true>;
+    rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kW * 32, smem);
+    if (rc != cudaSuccess) return rc;
+    long long grid = (long long)sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > kFusedGridMax) grid = kFusedGridMax;
+    if (grid > n_tiles) grid = n_tiles;
+    FusedEmit F;
+    F.out = d_out;
+    F.status = status;
+    F.ticket = tickets + slot;
+    F.total = total;
+    F.host_total = host_total;
+    F.spill = spill;
+    F.tile0 = lo / tile_bytes;
+    F.write_header = first ? 1 : 0;
+    kern<<<(unsigned)grid, kW * 32, smem, st>>>(d_in + lo, n_in, pre, P, hist_cap, n_tiles, nullptr,
+                                                nullptr, (uint16_t *)nullptr, 0, F);
     return cudaGetLastError();
 }
 
