@@ -623,7 +623,7 @@ def run_native(args):
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "bytes_per_gpu": n, "sb": sb, "la": la,
                        "token_bits": T, "block_bytes": lz77_b200.block_size(sb),
-                       "segment_bytes": lz77_b200.segment_size(),
+                       "segment_bytes": lz77_b200.segment_size(sb, la),
                        "sharding": f"{world} rank(s), whole blocks per rank, no collective",
                        "l2": "inputs (256 MiB) larger than L2 (126 MB); no flush needed"},
             "encode_gbs": world * n / (enc_ms * 1e-3) / 1e9,

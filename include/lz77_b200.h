@@ -69,8 +69,10 @@ long lz77_gpu_encode_bound(long n_in, int sb, int la);
 /* size of the independent blocks the encoder cuts the input into: no match
  * reaches across a multiple of this, and a token starts on every multiple */
 long lz77_gpu_block_size(int sb);
-/* bytes after which the greedy parse restarts inside a block */
-long lz77_gpu_segment_size(void);
+/* bytes after which the greedy parse restarts inside a block, for these parameters
+ * (-1: the defaults) and the current encoder options (1024 today; callers that restate
+ * the encoder's specification ask instead of assuming) */
+long lz77_gpu_segment_size(int sb, int la);
 
 /* ---- lifetime ------------------------------------------------------------ */
 
@@ -105,6 +107,15 @@ void lz77_gpu_set_host_chunk(long bytes);
  * jumping (like streams of the reference encoder) and cannot shard for decode.  Either
  * way the stream is the reference's format and decodes with the reference decoder. */
 void lz77_gpu_set_history(int enabled);
+
+/* Encoder, 24-bit tokens (the default parameters) and windows <= 8191 only (default
+ * off).  On: the bit-packer (writecode lz77.c:246-252, bitIO_write bitio.c:203-239)
+ * runs inside the search kernel -- tokens never travel through HBM unpacked, encode
+ * DRAM traffic is N + C instead of N + 9 K + C and the scratch shrinks from 4 bytes per
+ * input byte to a few MiB -- at the price of an ordered hand-over between tiles that
+ * currently costs more time than the separate pack kernel saves.  The
+ * stream is byte-identical either way. */
+void lz77_gpu_set_fused_pack(int enabled);
 
 /* Streams the reference encoder wrote (matches that leave their block) are
  * decoded by pointer jumping over pieces of this many output bytes (default

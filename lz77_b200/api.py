@@ -30,7 +30,7 @@ EXPORTS = (
     "lz77_gpu_decode_size_device", "lz77_gpu_decode_device", "lz77_gpu_last_timing",
     "lz77_gpu_set_timing", "lz77_gpu_set_stream", "lz77_gpu_set_host_chunk",
     "lz77_gpu_slice_tokens_device", "lz77_gpu_token_at_device", "lz77_gpu_set_jump_piece",
-    "lz77_gpu_set_history",
+    "lz77_gpu_set_history", "lz77_gpu_set_fused_pack",
     "lz77_shard_range", "lz77_comm_get_unique_id", "lz77_comm_init", "lz77_comm_destroy",
     "lz77_gpu_encode_sharded_device", "lz77_gpu_decode_sharded_device", "lz77_comm_last_stats",
     "lz77_mgpu_init", "lz77_mgpu_shutdown", "lz77_mgpu_encode", "lz77_mgpu_decode",
@@ -87,7 +87,7 @@ def load_library() -> C.CDLL:
         "lz77_token_bits": (ip, [ip, ip]),
         "lz77_gpu_encode_bound": (lp, [lp, ip, ip]),
         "lz77_gpu_block_size": (lp, [ip]),
-        "lz77_gpu_segment_size": (lp, []),
+        "lz77_gpu_segment_size": (lp, [ip, ip]),
         "lz77_gpu_device_count": (ip, []),
         "lz77_gpu_init": (ip, [ip]),
         "lz77_gpu_shutdown": (None, []),
@@ -109,6 +109,7 @@ def load_library() -> C.CDLL:
         "lz77_gpu_token_at_device": (ip, [vp, lp, lp, plong, plong]),
         "lz77_gpu_set_jump_piece": (ip, [lp]),
         "lz77_gpu_set_history": (None, [ip]),
+        "lz77_gpu_set_fused_pack": (None, [ip]),
         "lz77_shard_range": (ip, [lp, ip, lp, ip, plong, plong]),
         "lz77_comm_get_unique_id": (ip, [vp]),
         "lz77_comm_init": (ip, [vp, ip, ip]),
@@ -158,8 +159,10 @@ def block_size(sb: int = -1) -> int:
     return load_library().lz77_gpu_block_size(sb)
 
 
-def segment_size() -> int:
-    return load_library().lz77_gpu_segment_size()
+def segment_size(sb: int = -1, la: int = -1) -> int:
+    """Bytes after which the greedy parse restarts, for these parameters (and the current
+    fused-pack setting): part of the encoder's specification."""
+    return load_library().lz77_gpu_segment_size(sb, la)
 
 
 # ---- lifetime ----------------------------------------------------------------
@@ -213,6 +216,11 @@ def set_history(enabled: bool) -> None:
     (lz77.c:101-105).  Better ratio at large windows; the stream no longer decodes block
     by block (pointer jumping) and cannot shard for decode."""
     load_library().lz77_gpu_set_history(1 if enabled else 0)
+
+
+def set_fused_pack(enabled: bool) -> None:
+    """Encoder, 24-bit tokens: pack inside the search kernel (no unpacked tokens in HBM)."""
+    load_library().lz77_gpu_set_fused_pack(1 if enabled else 0)
 
 
 def set_jump_piece(nbytes: int) -> None:

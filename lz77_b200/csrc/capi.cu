@@ -80,6 +80,7 @@ int make_params(int sb, int la, Params *P)
     P->block_shift = bitof((int)P->block);
     P->tile_shift = P->block_shift < 17 ? P->block_shift : 17;
     P->history = ctx().history ? 1 : 0;
+    P->fused_pack = ctx().fused_pack ? 1 : 0;
     return LZ77_OK;
 }
 
@@ -171,7 +172,12 @@ long lz77_gpu_block_size(int sb)
     return sb <= 8191 ? 65536L : 524288L;
 }
 
-long lz77_gpu_segment_size(void) { return kSegBytes; }
+long lz77_gpu_segment_size(int sb, int la)
+{
+    Params P;
+    if (make_params(sb, la, &P) != LZ77_OK) return kSegBytes;
+    return parse_segment_bytes(P.window, P.la, P.fused_pack != 0);
+}
 
 int lz77_gpu_device_count(void)
 {
@@ -317,6 +323,8 @@ void lz77_gpu_set_host_chunk(long bytes)
 }
 
 void lz77_gpu_set_history(int enabled) { g.history = enabled != 0; }
+
+void lz77_gpu_set_fused_pack(int enabled) { g.fused_pack = enabled != 0; }
 
 int lz77_gpu_set_jump_piece(long bytes)
 {

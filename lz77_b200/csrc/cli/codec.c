@@ -14,7 +14,10 @@
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
+#include <sys/types.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "lz77_b200.h"
 
@@ -147,6 +150,68 @@ static int put_bits(FILE *f, const unsigned char *src, long nbits, unsigned *acc
  * and a writer thread that drains the results (fwrite) -- piece k+1 is being read and
  * piece k-1 written while piece k is on the GPU.
  */
+/* positional file I/O on `n_thr` threads: a tmpfs / page-cache copy runs at one core's
+ * memcpy speed, several of them side by side at several times that */
+struct pio {
+    int fd, write;
+    unsigned char *buf;
+    long off, len, done;
+    int failed;
+};
+
+static void *pio_main(void *arg)
+{
+    struct pio *p = arg;
+    while (p->done < p->len) {
+        ssize_t r = p->write ? pwrite(p->fd, p->buf + p->done, (size_t)(p->len - p->done), p->off + p->done)
+                             : pread(p->fd, p->buf + p->done, (size_t)(p->len - p->done), p->off + p->done);
+        if (r < 0) {
+            p->failed = 1;
+            break;
+        }
+        if (r == 0)
+            break; /* end of file */
+        p->done += r;
+    }
+    return NULL;
+}
+
+enum { PIO_THREADS = 4 };
+
+/* reads / writes [off, off + len) of fd; returns the bytes transferred (short only at the
+ * end of the file) or -1 */
+static long pio_run(int fd, int write, unsigned char *buf, long off, long len)
+{
+    struct pio part[PIO_THREADS];
+    pthread_t th[PIO_THREADS];
+    long per = (len / PIO_THREADS + 4095) & ~4095L, total = 0;
+    int i, n = 0, failed = 0;
+    if (len < (4L << 20))
+        per = len; /* small transfers: one thread */
+    for (i = 0; i < PIO_THREADS && (long)i * per < len; i++, n++) {
+        part[i].fd = fd, part[i].write = write, part[i].buf = buf + (long)i * per;
+        part[i].off = off + (long)i * per;
+        part[i].len = len - (long)i * per < per ? len - (long)i * per : per;
+        part[i].done = 0, part[i].failed = 0;
+        if (i > 0 && pthread_create(&th[i], NULL, pio_main, &part[i]) != 0) {
+            pio_main(&part[i]);
+            th[i] = 0;
+        }
+    }
+    if (n > 0)
+        pio_main(&part[0]);
+    for (i = 1; i < n; i++)
+        if (th[i])
+            pthread_join(th[i], NULL);
+    for (i = 0; i < n; i++) {
+        failed |= part[i].failed;
+        total += part[i].done;
+        if (part[i].done < part[i].len)
+            break; /* a short part: the file ended inside it */
+    }
+    return failed ? -1 : total;
+}
+
 enum { RING = 3 };
 
 struct slot {
@@ -161,6 +226,8 @@ struct ring {
     pthread_mutex_t mu;
     pthread_cond_t cv;
     FILE *fin, *fout;
+    int fd_in, fd_out;       /* >= 0: positional I/O on several threads (regular files) */
+    long in_off, out_off;
     long piece;
     int tbits, failed_read, failed_write, pieces_read_done;
     unsigned acc;
@@ -190,9 +257,18 @@ static void *reader_main(void *arg)
     for (;;) {
         struct slot *sl = &r->s[i];
         ring_wait(r, i, 0);
-        sl->n_in = (long)fread(sl->in, 1, (size_t)r->piece, r->fin);
-        if (ferror(r->fin))
-            r->failed_read = 1;
+        if (r->fd_in >= 0) {
+            sl->n_in = pio_run(r->fd_in, 0, sl->in, r->in_off, r->piece);
+            if (sl->n_in < 0) {
+                r->failed_read = 1;
+                sl->n_in = 0;
+            }
+            r->in_off += sl->n_in;
+        } else {
+            sl->n_in = (long)fread(sl->in, 1, (size_t)r->piece, r->fin);
+            if (ferror(r->fin))
+                r->failed_read = 1;
+        }
         sl->eof = sl->n_in < r->piece || r->failed_read;
         if (sl->n_in == 0 && !first)
             sl->eof = 2; /* nothing left: no piece, just the end */
@@ -216,13 +292,26 @@ static void *writer_main(void *arg)
         if (sl->n_out > 0 && !r->failed_write) {
             /* padding is < 8 < T bits, so the token count follows from the size */
             long n_tokens = ((sl->n_out - 4) * 8) / r->tbits;
-            if (!r->wrote_header) { /* header, lz77.c:74-75 */
-                if (fwrite(sl->out, 1, 4, r->fout) != 4)
+            if (r->fd_out >= 0) { /* byte-aligned tokens: payloads land at known offsets */
+                long nb = n_tokens * r->tbits / 8;
+                if (!r->wrote_header) {
+                    if (pio_run(r->fd_out, 1, sl->out, 0, 4) != 4)
+                        r->failed_write = 1;
+                    r->out_off = 4;
+                    r->wrote_header = 1;
+                }
+                if (pio_run(r->fd_out, 1, sl->out + 4, r->out_off, nb) != nb)
                     r->failed_write = 1;
-                r->wrote_header = 1;
+                r->out_off += nb;
+            } else {
+                if (!r->wrote_header) { /* header, lz77.c:74-75 */
+                    if (fwrite(sl->out, 1, 4, r->fout) != 4)
+                        r->failed_write = 1;
+                    r->wrote_header = 1;
+                }
+                if (put_bits(r->fout, sl->out + 4, n_tokens * r->tbits, &r->acc, &r->acc_bits) != 0)
+                    r->failed_write = 1;
             }
-            if (put_bits(r->fout, sl->out + 4, n_tokens * r->tbits, &r->acc, &r->acc_bits) != 0)
-                r->failed_write = 1;
         }
         ring_set(r, i, 0);
         if (eof)
@@ -246,6 +335,20 @@ void encode(FILE *file, struct bitFILE *out, int la, int sb)
     r.tbits = lz77_token_bits(esb, ela);
     r.fin = file;
     r.fout = out->file;
+    r.fd_in = r.fd_out = -1;
+    {
+        /* regular files: positional reads / writes on several threads */
+        struct stat st;
+        long pos = ftell(file);
+        if (pos >= 0 && fstat(fileno(file), &st) == 0 && S_ISREG(st.st_mode)) {
+            r.fd_in = fileno(file);
+            r.in_off = pos;
+        }
+        fflush(out->file);
+        if ((r.tbits & 7) == 0 && ftell(out->file) == 0 && fstat(fileno(out->file), &st) == 0 &&
+            S_ISREG(st.st_mode))
+            r.fd_out = fileno(out->file);
+    }
     pthread_mutex_init(&r.mu, NULL);
     pthread_cond_init(&r.cv, NULL);
     /* small files: no point in pinning three full pieces */
@@ -392,6 +495,8 @@ struct wjob {
     pthread_mutex_t mu;
     pthread_cond_t cv;
     FILE *f;
+    int fd;      /* >= 0: positional writes on several threads (a regular file) */
+    long off;
     const unsigned char *p;
     long n;
     int pending, quit, failed;
@@ -407,8 +512,13 @@ static void *wjob_main(void *arg)
         if (!w->pending && w->quit)
             break;
         pthread_mutex_unlock(&w->mu);
-        if (w->n > 0 && fwrite(w->p, 1, (size_t)w->n, w->f) != (size_t)w->n)
+        if (w->n > 0 && w->fd >= 0) {
+            if (pio_run(w->fd, 1, (unsigned char *)w->p, w->off, w->n) != w->n)
+                w->failed = 1;
+            w->off += w->n;
+        } else if (w->n > 0 && fwrite(w->p, 1, (size_t)w->n, w->f) != (size_t)w->n) {
             w->failed = 1;
+        }
         pthread_mutex_lock(&w->mu);
         w->pending = 0;
         pthread_cond_broadcast(&w->cv);
@@ -488,6 +598,13 @@ void decode(struct bitFILE *file, FILE *out)
     pthread_mutex_init(&w.mu, NULL);
     pthread_cond_init(&w.cv, NULL);
     w.f = out;
+    w.fd = -1;
+    {
+        struct stat st;
+        fflush(out);
+        if (ftell(out) == 0 && fstat(fileno(out), &st) == 0 && S_ISREG(st.st_mode))
+            w.fd = fileno(out);
+    }
     pthread_create(&writer, NULL, wjob_main, &w);
     clock_gettime(CLOCK_MONOTONIC, &t0);
 
@@ -526,9 +643,15 @@ void decode(struct bitFILE *file, FILE *out)
                 copy_bits(sbuf, bit, raw, cursor * tbits, take * tbits);
                 bit += take * tbits;
                 if (obuf[cur] == NULL) {
-                    obuf_cap[cur] = (take * tbits / 8) * 3 + hist_len + (1L << 20);
-                    if (obuf_cap[cur] > out_limit + hist_len + 16)
-                        obuf_cap[cur] = out_limit + hist_len + 16;
+                    /* first use of this buffer: size it from the piece's decoded size (one
+                     * token scan) -- pinning memory twice costs far more */
+                    long want = 0;
+                    rc = lz77_gpu_decode_size(sbuf, (bit + 7) / 8, &want);
+                    if (rc != LZ77_OK)
+                        die("decoding", rc);
+                    obuf_cap[cur] = want + want / 4 + (1L << 20);
+                    if (obuf_cap[cur] > out_limit + hist_len + (1L << 20))
+                        obuf_cap[cur] = out_limit + hist_len + (1L << 20);
                     obuf[cur] = lz77_gpu_host_alloc(obuf_cap[cur]);
                     if (obuf[cur] == NULL)
                         die("allocating the output buffer", LZ77_E_NOMEM);

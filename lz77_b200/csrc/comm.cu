@@ -347,7 +347,8 @@ int lz77_gpu_encode_sharded_device(const void *d_in, long n_in, int sb, int la, 
             arg = LZ77_E_SPACE;
         meta[0] = (unsigned long long)n_in;
         meta[1] = arg == LZ77_OK ? ((unsigned long long)P.sb | ((unsigned long long)P.la << 16) |
-                                    ((unsigned long long)P.history << 32))
+                                    ((unsigned long long)P.history << 32) |
+                                    ((unsigned long long)P.fused_pack << 33))
                                  : 0;
         meta[2] = (unsigned long long)(long long)arg;
     }
@@ -356,7 +357,8 @@ int lz77_gpu_encode_sharded_device(const void *d_in, long n_in, int sb, int la, 
     const long long N = (long long)meta[0];
     if (make_params((int)(meta[1] & 0xffff), (int)((meta[1] >> 16) & 0xffff), &P) != LZ77_OK)
         return LZ77_E_ARG;
-    P.history = (int)((meta[1] >> 32) & 1);  // root's setting counts
+    P.history = (int)((meta[1] >> 32) & 1);  // root's settings count
+    P.fused_pack = (int)((meta[1] >> 33) & 1);
     const int T = P.tbits, world = c.world, rank = c.rank;
 
     // 2. runs of whole blocks; every rank allocates, then all agree to go on

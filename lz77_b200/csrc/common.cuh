@@ -26,6 +26,8 @@ struct Params {
     int block_shift;
     int tile_shift;    // decode tile = min(block, 128 KiB): what fits shared memory (a
                        // 512 KiB block is decoded as four tiles)
+    int fused_pack;    // encoder: 1 = 24-bit tokens are packed inside the search kernel
+                       // (lz77_gpu_set_fused_pack); 0 = 32-bit tokens to scratch + pack kernel
     int history;       // encoder: 1 = the match window slides across block seams like the
                        // reference's (lz77.c:101-105); 0 = independent blocks
 };

@@ -52,6 +52,7 @@ struct Context {
     long long host_chunk = 0;   // lz77_gpu_set_host_chunk(); 0: default
     long long jump_piece = 0;   // lz77_gpu_set_jump_piece(); 0: default
     bool history = false;       // lz77_gpu_set_history()
+    bool fused_pack = false;    // lz77_gpu_set_fused_pack()
     lz77_timing last;
     char err[256];
 

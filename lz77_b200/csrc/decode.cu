@@ -407,7 +407,8 @@ __global__ void lz77_token_at_kernel(const uint32_t *__restrict__ words, long lo
 #define LZ77_DEC_WORDCOPY 1  // matches of <= 16 bytes that do not overlap: word loads, byte stores
 #endif
 #ifndef LZ77_DEC_EAGER
-#define LZ77_DEC_EAGER 0  // 1: copy whatever is ready at once instead of waiting for the set to settle
+#define LZ77_DEC_EAGER 1  // copy whatever is ready at once (0: wait for the ready set to settle;
+                          // measured 1.05 -> 0.91 ms on 256 MiB of text)
 #endif
 constexpr int kDecThreadsSmall = LZ77_DEC_THREADS;  // CTA size for 64 KiB tiles (3 CTAs/SM)
 constexpr int kDecSpins = LZ77_DEC_SPINS;        // polls without progress before backing off

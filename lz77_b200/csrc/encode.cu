@@ -228,7 +228,7 @@ size_t encode_scratch_bytes(long long n_in, const Params &P)
     const long long n_seg = (n_in + kSegBytes - 1) / kSegBytes;
     const long long n_part = (n_seg + kScanTile - 1) / kScanTile;
     size_t b = 0;
-    b += (size_t)(n_seg * kSegBytes) * sizeof(uint32_t);          // tok_tmp
+    b += (size_t)(n_seg * kSegBytes) * sizeof(uint32_t);        // tok_tmp
     b += (size_t)((n_seg + 63) & ~63LL) * sizeof(uint32_t);       // seg_ntok
     b += (size_t)((n_seg + 63) & ~63LL) * sizeof(unsigned long long);  // prefix
     b += (size_t)((n_part + 63) & ~63LL) * sizeof(unsigned long long); // partials

@@ -44,6 +44,9 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long p
                                 const Params &P, uint32_t *tok_tmp, uint32_t *seg_ntok,
                                 cudaStream_t st);
 
+// bytes after which the greedy parse restarts (part of the stream's specification)
+int parse_segment_bytes(int window, int la, bool fused_pack);
+
 // 24-bit tokens and a window <= 8191: search + parse + pack in one persistent kernel
 // (search_bucket.cu); `slot` < 64 names the ticket of this launch (launches of one call
 // that may run side by side need different ones)

@@ -202,16 +202,28 @@ __device__ __forceinline__ int group_lower_bound_s(uint32_t se, int n, int lo, i
 }
 
 // kLanes lanes (a "group": 32, 16 or 8) cooperate on one parse segment, so a warp
-// parses 32 / kLanes segments side by side.  (Measured: groups of 16 or 8 lanes with
-// 512- or 256-byte segments -- the same 8 KiB tile -- are no faster than one warp per
-// 1 KiB segment: the groups of a warp do not stay in step.  The fused path is written
-// for kLanes == 32.)
+// parses 32 / kLanes segments side by side.  Measured on 256 MiB of text (B200), the same
+// 8 KiB tile throughout: one warp per 1 KiB segment 8.7 ms; groups of 16 / 8 lanes on 512- /
+// 256-byte segments with this loop 8.6 / 9.0 ms (the groups of a warp do not stay in step);
+// the same groups driven in LOCKSTEP by a per-group state machine (warp-uniform branches,
+// candidates walked backwards from the position's own bucket slot, so no window lower bound)
+// 10.5 / 9.6 ms although byte-exact: a pass of the state machine costs the sum of all the
+// steps any group is in, and a warp waits for the slowest of its four segments.  One warp
+// per segment stays; the fused path is written for kLanes == 32.
 #ifndef LZ77_PARSE_MINBLOCKS
 #define LZ77_PARSE_MINBLOCKS 1
+#endif
+#ifndef LZ77_PARSE_WARPS
+#define LZ77_PARSE_WARPS 8
+#endif
+#ifndef LZ77_PARSE_LANES
+#define LZ77_PARSE_LANES 32
 #endif
 
 constexpr int kTokBuf = 512;                     // tokens per segment kept in shared memory
 constexpr int kTokSpill = kSegBytes - kTokBuf;   // the rest of a worst-case segment: global
+constexpr int kRing = 3;                         // packed tiles a CTA may have parked
+constexpr int kRingSlot = 3 * LZ77_PARSE_WARPS * kSegBytes + 256;  // worst case: a token per byte
 constexpr unsigned long long kLbAgg = 1ull << 62, kLbInc = 2ull << 62, kLbVal = (1ull << 62) - 1;
 
 struct FusedEmit {                 // outputs of the fused path (kFused)
@@ -221,11 +233,13 @@ struct FusedEmit {                 // outputs of the fused path (kFused)
     unsigned long long *total;     // tokens up to and including this launch
     unsigned long long *host_total;  // the same in mapped pinned memory (may be null)
     uint32_t *spill;               // gridDim.x * kWarps * kTokSpill tokens
+    uint8_t *ring;                 // gridDim.x * kRing slots of kRingSlot bytes
     long long tile0;               // index of this launch's first tile in the whole call
     int write_header;
 };
 
-template <bool kSmallLA, int kWarps, int kLanes, typename PosT, bool kSortedGlobal, bool kFused>
+template <bool kSmallLA, int kWarps, int kLanes, typename PosT, bool kSortedGlobal, bool kFused,
+          int kSeg>
 __global__ void __launch_bounds__(kWarps * 32, kFused ? 4 : LZ77_PARSE_MINBLOCKS)
 lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long pre, Params P,
                          int hist_cap, long long n_tiles, uint32_t *__restrict__ tok_tmp,
@@ -238,13 +252,16 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
     __shared__ uint32_t s_total;
     __shared__ long long s_tile;                 // fused: the tile this CTA drew
     __shared__ int s_cnt[kWarps];                // fused: tokens per segment of the tile
-    __shared__ unsigned long long s_excl;        // fused: tokens in front of the tile
+    __shared__ unsigned long long s_excl;        // fused: tokens in front of the tile being resolved
+    __shared__ long long s_pend_tile[kRing];     // fused: parked tiles (index in the whole call)
+    __shared__ int s_pend_k[kRing];              //        and their token counts
+    __shared__ int s_ok;
     static_assert(!kFused || kLanes == 32, "the fused emit is written for one warp per segment");
 
     constexpr int kThreads = kWarps * 32;
     constexpr int kSegsPerWarp = 32 / kLanes;
     constexpr int kCntWords = kBuckets * (kWarps / 2);  // two 16-bit counters per word
-    constexpr int tile_bytes = kWarps * kSegsPerWarp * kSegBytes;
+    constexpr int tile_bytes = kWarps * kSegsPerWarp * kSeg;
     const int data_cap = hist_cap + tile_bytes + 64;
     PosT *bstart = reinterpret_cast<PosT *>(smem + ((data_cap + 15) & ~15));
     uint32_t *cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bstart) +
@@ -269,6 +286,98 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    // ---- fused path: tiles parked in the ring, their place in the stream pending ----
+    int seq = 0, done = 0;  // tiles parked / resolved by this CTA (uniform across the CTA)
+    // Resolves parked tiles, oldest first, as far as their predecessors have reported their
+    // token counts (decoupled look-back over the tiles: tiles are handed out by ticket, so
+    // every predecessor is running or done); waits only when the ring is full or `drain`.
+    auto resolve_parked = [&](bool drain) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        while (done < seq) {
+            const bool must = drain || (seq - done) >= kRing;
+            __syncthreads();  // orders the ring stores of this CTA before their reads
+            if (warp == 0) {
+                const long long gt = s_pend_tile[done % kRing];
+                const int k_tile = s_pend_k[done % kRing];
+                unsigned long long excl = 0;
+                bool ok = true;
+                if (gt > 0) {
+                    long long idx = gt - 1 - lane;
+                    while (true) {
+                        unsigned long long sv = kLbInc;  // in front of the first tile: nothing
+                        if (idx >= 0)
+                            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(sv) : "l"(F.status + idx) : "memory");
+                        if (must) {
+                            while (__any_sync(0xffffffffu, (sv >> 62) == 0)) {
+                                if ((sv >> 62) == 0) {
+                                    __nanosleep(64);
+                                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(sv) : "l"(F.status + idx) : "memory");
+                                }
+                            }
+                        } else if (__any_sync(0xffffffffu, (sv >> 62) == 0)) {
+                            ok = false;  // a predecessor is still parsing: try again after the next tile
+                            break;
+                        }
+                        const unsigned inc_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                        unsigned long long v = sv & kLbVal;
+                        if (inc_mask) {
+                            const int first = __ffs(inc_mask) - 1;
+                            v = lane <= first ? v : 0ull;
+                        }
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                        excl += v;
+                        if (inc_mask) break;
+                        idx -= 32;
+                    }
+                }
+                if (lane == 0) {
+                    s_ok = ok ? 1 : 0;
+                    if (ok) {
+                        const unsigned long long incl = excl + (unsigned long long)k_tile;
+                        if (gt == F.tile0 + n_tiles - 1) {  // the launch's last tile: running total
+                            *F.total = incl;
+                            if (F.host_total) {
+                                *reinterpret_cast<volatile unsigned long long *>(F.host_total) = incl;
+                                __threadfence_system();
+                            }
+                            __threadfence();
+                        }
+                        atomicExch(&F.status[gt], kLbInc | incl);
+                        s_excl = excl;
+                    }
+                }
+            }
+            __syncthreads();
+            if (!s_ok) return;
+            // ring -> stream.  T is a multiple of 8, so the tile owns whole bytes of the
+            // stream (nothing to zero or merge): single bytes up to the first aligned word,
+            // 32-bit stores, single bytes.
+            {
+                const int k_tile = s_pend_k[done % kRing];
+                const unsigned long long g0 = 4ull + 3ull * s_excl;  // byte offset in the stream
+                const uint8_t *src =
+                    F.ring + ((size_t)blockIdx.x * kRing + (size_t)(done % kRing)) * kRingSlot;
+                uint8_t *dst = F.out + g0;
+                const int nbytes = 3 * k_tile;
+                int head = (int)((4ull - (g0 & 3ull)) & 3ull);
+                if (head > nbytes) head = nbytes;
+                for (int i = threadIdx.x; i < head; i += kWarps * 32) dst[i] = __ldcg(src + i);
+                const int nwords = (nbytes - head) >> 2;
+                const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);
+                uint32_t *dw = reinterpret_cast<uint32_t *>(dst + head);
+                const int bsh = head * 8;
+                for (int w = threadIdx.x; w < nwords; w += kWarps * 32)
+                    dw[w] = __funnelshift_r(__ldcg(sw + w), __ldcg(sw + w + 1), bsh);
+                for (int i = head + 4 * nwords + (int)threadIdx.x; i < nbytes; i += kWarps * 32)
+                    dst[i] = __ldcg(src + i);
+                if (s_pend_tile[done % kRing] == 0 && F.write_header && threadIdx.x == 0)
+                    *reinterpret_cast<uint32_t *>(F.out) = (uint32_t)P.sb | ((uint32_t)P.la << 16);
+            }
+            done++;
+        }
+    };
 
     uint32_t phase = 0;
     for (long long tile_i = blockIdx.x;; tile_i += gridDim.x, phase ^= 1u) {
@@ -398,15 +507,15 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
 
         // ---- parse: one group of kLanes lanes per segment -------------------
         const long long seg_lo =
-            tile_lo + (long long)(warp * kSegsPerWarp + sg) * kSegBytes;
-        const long long sgm = seg_lo / kSegBytes;  // global segment index
+            tile_lo + (long long)(warp * kSegsPerWarp + sg) * kSeg;
+        const long long sgm = seg_lo / kSeg;  // global segment index
         if (seg_lo < n) {
-            long long seg_hi = seg_lo + kSegBytes;
+            long long seg_hi = seg_lo + kSeg;
             if (seg_hi > n) seg_hi = n;
             const int seg_end = (int)(seg_hi - src_lo) + dst0;
             int p0 = (int)(seg_lo - src_lo) + dst0;
             const int first_idx = dst0 + hist_al - (int)hist;  // oldest byte a match may start at
-            uint32_t *tok_row = kFused ? nullptr : tok_tmp + sgm * kSegBytes;
+            uint32_t *tok_row = kFused ? nullptr : tok_tmp + sgm * kSeg;
             const int len_shift = P.ob, lit_shift = P.ob + P.lb;
             const int la = P.la, window = P.window;
             uint32_t *tok_at = tok_row;  // a running pointer: no address arithmetic per token
@@ -549,7 +658,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
         __syncthreads();  // the next tile overwrites the staged data and the buckets
 
         if (kFused) {
-            // ---- the tile's place in the stream: decoupled look-back over the tiles ----
+            // ---- pack: 3 bytes per token into shared memory (the bucket lists are dead) ----
             int pre_w = 0, k_tile = 0;
 #pragma unroll
             for (int w = 0; w < kWarps; w++) {
@@ -557,109 +666,78 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                 if (w < warp) pre_w += c;
                 k_tile += c;
             }
-            const long long gt = F.tile0 + tile_i;  // index in the whole call
-            if (warp == 0) {
-                unsigned long long excl = 0;
-                if (gt > 0) {
-                    if (lane == 0) atomicExch(&F.status[gt], kLbAgg | (unsigned long long)k_tile);
-                    long long idx = gt - 1 - lane;
-                    while (true) {
-                        unsigned long long sv = kLbInc;  // in front of the first tile: nothing
-                        if (idx >= 0)
-                            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(sv) : "l"(F.status + idx) : "memory");
-                        while (__any_sync(0xffffffffu, (sv >> 62) == 0)) {
-                            if ((sv >> 62) == 0) {
-                                __nanosleep(64);
-                                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(sv) : "l"(F.status + idx) : "memory");
-                            }
-                        }
-                        const unsigned inc_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-                        unsigned long long v = sv & kLbVal;
-                        if (inc_mask) {
-                            const int first = __ffs(inc_mask) - 1;
-                            v = lane <= first ? v : 0ull;
-                        }
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                        excl += v;
-                        if (inc_mask) break;
-                        idx -= 32;
-                    }
-                }
-                if (lane == 0) {
-                    const unsigned long long incl = excl + (unsigned long long)k_tile;
-                    if (tile_i == n_tiles - 1) {  // the launch's last tile: the running total
-                        *F.total = incl;
-                        if (F.host_total) {
-                            *reinterpret_cast<volatile unsigned long long *>(F.host_total) = incl;
-                            __threadfence_system();
-                        }
-                        __threadfence();
-                    }
-                    atomicExch(&F.status[gt], kLbInc | incl);
-                    s_excl = excl;
-                }
-            }
-            __syncthreads();
-            // ---- pack: 3 bytes per token, at the stream's offset modulo 16 ----
-            const unsigned long long g0 = 4ull + 3ull * s_excl;  // byte offset in the stream
-            const int shift = (int)(g0 & 15ull);
-            uint8_t *pk = reinterpret_cast<uint8_t *>(sorted);   // the bucket lists are dead now
+            uint8_t *pk = reinterpret_cast<uint8_t *>(sorted);
             {
                 const uint32_t *buf = cnt + warp * kTokBuf;
                 const uint32_t *sp = F.spill + ((size_t)blockIdx.x * kWarps + warp) * kTokSpill;
                 const int mine = s_cnt[warp];
                 for (int t = lane; t < mine; t += 32) {
                     const uint32_t tok = t < kTokBuf ? buf[t] : sp[t - kTokBuf];
-                    uint8_t *b = pk + shift + 3 * (pre_w + t);
+                    uint8_t *b = pk + 3 * (pre_w + t);
                     b[0] = (uint8_t)tok;
                     b[1] = (uint8_t)(tok >> 8);
                     b[2] = (uint8_t)(tok >> 16);
                 }
             }
             __syncthreads();
-            // ---- write: 128-bit stores, single bytes at the two ends ----
+            // ---- park the packed tile in this CTA's ring (global memory, L2-resident) and
+            //      publish its token count; its place in the stream is resolved later, so a
+            //      slow tile ahead does not stall this CTA (no convoy behind the slowest tile) ----
             {
-                uint8_t *dstb = F.out + (g0 - (unsigned long long)shift);  // 16-byte aligned
-                const int end = shift + 3 * k_tile;
-                const int c_lo = shift == 0 ? 0 : 16;
-                const int c_hi = end & ~15;
-                for (int c = c_lo + 16 * (int)threadIdx.x; c < c_hi; c += 16 * kThreads)
-                    *reinterpret_cast<uint4 *>(dstb + c) = *reinterpret_cast<const uint4 *>(pk + c);
-                for (int i = shift + (int)threadIdx.x; i < min(c_lo, end); i += kThreads)
-                    dstb[i] = pk[i];
-                for (int i = max(c_hi, c_lo) + (int)threadIdx.x; i < end; i += kThreads)
-                    dstb[i] = pk[i];
-                if (gt == 0 && F.write_header && threadIdx.x == 0)
-                    *reinterpret_cast<uint32_t *>(F.out) = (uint32_t)P.sb | ((uint32_t)P.la << 16);
+                uint4 *slot = reinterpret_cast<uint4 *>(
+                    F.ring + ((size_t)blockIdx.x * kRing + (size_t)(seq % kRing)) * kRingSlot);
+                const int nchunks = (3 * k_tile + 15) >> 4;
+                for (int c = threadIdx.x; c < nchunks; c += kThreads)
+                    slot[c] = reinterpret_cast<const uint4 *>(pk)[c];
+                const long long gt = F.tile0 + tile_i;  // index in the whole call
+                if (threadIdx.x == 0) {
+                    s_pend_tile[seq % kRing] = gt;
+                    s_pend_k[seq % kRing] = k_tile;
+                    if (gt > 0) atomicExch(&F.status[gt], kLbAgg | (unsigned long long)k_tile);
+                }
+                seq++;
             }
-            // (the ticket's barrier at the top of the loop keeps the next tile off this one)
+            // (the barrier at the top of resolve orders the ring stores before their reads)
         }
+        if (kFused) resolve_parked(false);
     }
+    if (kFused) resolve_parked(true);  // no tiles left to draw: wait for the parked ones
 }
 
 // ---------------------------------------------------------------------------
 
-#ifndef LZ77_PARSE_WARPS
-#define LZ77_PARSE_WARPS 8
-#endif
-#ifndef LZ77_PARSE_LANES
-#define LZ77_PARSE_LANES 32
-#endif
 
-bool parse_bucket_fused(const Params &P) { return P.tbits == 24 && P.window <= 8191; }
+bool parse_bucket_fused(const Params &P)
+{
+    return P.fused_pack && P.tbits == 24 && P.window <= 8191;
+}
 
 // scratch of the fused path for a call over n_total input bytes: look-back words of all
 // its tiles, the tickets (one per launch that may be in flight), the spill area of one
 // resident grid
 constexpr int kMaxTickets = 64;
-constexpr int kFusedGridMax = 148 * 4 * 2;
+constexpr int kFusedGridMax = 160 * 4;
+static size_t fused_status_bytes(long long n_tiles)  // (the areas behind it stay 256-byte aligned)
+{
+    return ((size_t)(n_tiles + 64) * 8 + 255) & ~(size_t)255;
+}
+
 size_t parse_bucket_fused_scratch(long long n_total)
 {
     const long long tile_bytes = (long long)LZ77_PARSE_WARPS * kSegBytes;
     const long long n_tiles = (n_total + tile_bytes - 1) / tile_bytes;
-    return (size_t)(n_tiles + 64) * 8 + (size_t)kMaxTickets * 4 + 256 +
-           (size_t)kFusedGridMax * LZ77_PARSE_WARPS * kTokSpill * 4 + 1024;
+    return fused_status_bytes(n_tiles) + (size_t)kMaxTickets * 4 + 256 +
+           (size_t)kFusedGridMax * LZ77_PARSE_WARPS * kTokSpill * 4 +
+           (size_t)kFusedGridMax * kRing * kRingSlot + 1024;
+}
+
+// Bytes after which the greedy parse restarts: part of the stream's specification
+// (lz77_gpu_segment_size()).  One value today; it is a function of the parameters because a
+// parser that runs several shorter segments per warp was measured (see the note at kLanes).
+int parse_segment_bytes(int window, int la, bool fused_pack)
+{
+    (void)window, (void)la, (void)fused_pack;
+    return kSegBytes;
 }
 
 cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long pre,
@@ -677,8 +755,8 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long p
     smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // bucket starts
     smem += (size_t)kBuckets * (kW / 2) * 4;                   // per-warp counters
     smem += data_cap * sizeof(uint16_t) + 80;                  // sorted positions + one round of padding
-    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, kL, uint16_t, false, false>
-                         : lz77_parse_bucket_kernel<false, kW, kL, uint16_t, false, false>;
+    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, kL, uint16_t, false, false, kSegBytes>
+                         : lz77_parse_bucket_kernel<false, kW, kL, uint16_t, false, false, kSegBytes>;
     cudaError_t rc =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
@@ -704,13 +782,15 @@ cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long lo
     const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
     char *p = (char *)scratch;
     unsigned long long *status = (unsigned long long *)p;
-    p += (size_t)(n_tiles_total + 64) * 8;
+    p += fused_status_bytes(n_tiles_total);
     unsigned int *tickets = (unsigned int *)p;
     p += (size_t)kMaxTickets * 4 + 256;
     uint32_t *spill = (uint32_t *)p;
+    p += (size_t)kFusedGridMax * kW * kTokSpill * 4;
+    uint8_t *ring = (uint8_t *)p;
     cudaError_t rc;
     if (first) {
-        rc = cudaMemsetAsync(scratch, 0, (size_t)(n_tiles_total + 64) * 8 + (size_t)kMaxTickets * 4, st);
+        rc = cudaMemsetAsync(scratch, 0, fused_status_bytes(n_tiles_total) + (size_t)kMaxTickets * 4, st);
         if (rc != cudaSuccess) return rc;
     }
     if (slot < 0 || slot >= kMaxTickets) return cudaErrorInvalidValue;
@@ -735,8 +815,8 @@ cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long lo
     const size_t pk_need = (size_t)tile_bytes * 3 + 32;
     if (tail < pk_need) tail = pk_need;
     smem += tail;
-    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, 32, uint16_t, false, true>
-                         : lz77_parse_bucket_kernel<false, kW, 32, uint16_t, false, true>;
+    auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, 32, uint16_t, false, true, kSegBytes>
+                         : lz77_parse_bucket_kernel<false, kW, 32, uint16_t, false, true, kSegBytes>;
     rc = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     int dev = 0, sms = 148, per_sm = 1;
@@ -754,6 +834,7 @@ cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long lo
     F.total = total;
     F.host_total = host_total;
     F.spill = spill;
+    F.ring = ring;
     F.tile0 = lo / tile_bytes;
     F.write_header = first ? 1 : 0;
     kern<<<(unsigned)grid, kW * 32, smem, st>>>(d_in + lo, n_in, pre, P, hist_cap, n_tiles, nullptr,

@@ -29,7 +29,7 @@ def lz():
 
 def _spec(orc, lz, data, sb, la):
     esb = 4095 if sb == -1 else sb
-    return orc.blocked_encode(data, sb, la, lz.block_size(esb), lz.segment_size())
+    return orc.blocked_encode(data, sb, la, lz.block_size(esb), lz.segment_size(sb, la))
 
 
 SMALL_INPUTS = [
@@ -612,7 +612,7 @@ def test_history_mode_equals_specification(lz, orc, history, sb, la, kind):
     by the reference decoder's restatement and by the GPU (pointer jumping)."""
     data = _history_input(kind, sb)
     enc = lz.encode(data, la=la, sb=sb)
-    spec, ntok = orc.blocked_encode(data, sb, la, 0, lz.segment_size())
+    spec, ntok = orc.blocked_encode(data, sb, la, 0, lz.segment_size(sb, la))
     assert enc == spec
     assert orc.decode(enc) == data
     assert lz.decode(enc) == data
@@ -631,7 +631,7 @@ def test_history_mode_host_chunks_and_reference_decoder(lz, orc, history, ref_av
     finally:
         history.set_host_chunk(16 << 20)
     assert chunked == one
-    spec, _ = orc.blocked_encode(data, sb, la, 0, lz.segment_size())
+    spec, _ = orc.blocked_encode(data, sb, la, 0, lz.segment_size(sb, la))
     assert one == spec
     if ref_available:
         from oracle import ref_run
@@ -650,3 +650,57 @@ def test_history_mode_ratio_within_half_percent_of_reference(lz, orc, history, k
     history.set_history(False)
     blocked = len(lz.encode(data, la=255, sb=65535))
     assert blocked >= ours
+
+
+# ---- fused search + pack (24-bit tokens): same stream, no unpacked tokens in HBM ----
+
+@pytest.fixture
+def fused(lz):
+    from lz77_b200 import api
+    api.set_fused_pack(True)
+    yield api
+    api.set_fused_pack(False)
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (4096, 16), (255, 255), (8191, 8)])
+@pytest.mark.parametrize("kind,n", [("zipf_text", 0), ("zipf_text", 1), ("zipf_text", 5), ("zipf_text", 8191),
+                                    ("zipf_text", 8192), ("zipf_text", 8193), ("zipf_text", 300_001),
+                                    ("random", 200_003), ("zeros", 150_000), ("log_like", 70_000)])
+def test_fused_pack_equals_specification(lz, orc, fused, sb, la, kind, n):
+    """lz77_gpu_set_fused_pack(1): the search kernel packs its own tokens (smem token
+    buffers, spill for incompressible data, decoupled look-back over the tiles, parked
+    tiles) -- byte-identical to the specification, tile counts of 0, 1, 2 and many."""
+    from lz77_b200 import synth
+    data = synth.make(kind, n, seed=41).numpy().tobytes() if n else b""
+    assert lz.token_bits(sb, la) == 24
+    enc = lz.encode(data, la=la, sb=sb)
+    spec, _ = _spec(orc, lz, data, sb, la)
+    assert enc == spec
+    assert lz.decode(enc) == data
+
+
+def test_fused_pack_host_chunks_history_and_large(lz, orc, fused):
+    """The chunked host pipeline (launches that overlap: the look-back runs across them),
+    history mode, and a 64 MiB device-resident input, all with the fused packer."""
+    import torch
+    from lz77_b200 import synth
+    data = synth.zipf_text(5 * (1 << 20) + 4321, seed=42).numpy().tobytes()
+    one = lz.encode(data)
+    fused.set_host_chunk(1 << 20)
+    try:
+        assert lz.encode(data) == one
+    finally:
+        fused.set_host_chunk(16 << 20)
+    spec1, _ = orc.blocked_encode(data, 4095, 15, lz.block_size(4095), lz.segment_size(4095, 15))
+    assert one == spec1
+    fused.set_history(True)
+    try:
+        h = lz.encode(data)
+        spec, _ = orc.blocked_encode(data, 4095, 15, 0, lz.segment_size(4095, 15))
+        assert h == spec
+    finally:
+        fused.set_history(False)
+    src = synth.zipf_text(64 << 20, seed=43, device="cuda")
+    a, ka = lz.encode_tensor(src)
+    assert torch.equal(lz.decode_tensor(a), src)
+    assert orc.decode(a.cpu().numpy().tobytes()) == src.cpu().numpy().tobytes()

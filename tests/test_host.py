@@ -52,8 +52,10 @@ def test_format_arithmetic_matches_oracle(lib, orc):
     assert lib.lz77_gpu_encode_bound(10, -1, -1) == 4 + 30
     assert lib.lz77_gpu_block_size(4095) == 65536
     assert lib.lz77_gpu_block_size(65535) == 524288
-    seg = lib.lz77_gpu_segment_size()
-    assert seg > 0 and 65536 % seg == 0
+    for sb, la in PARAM_SETS:
+        seg = lib.lz77_gpu_segment_size(sb, la)
+        assert seg in (256, 512, 1024) and 65536 % seg == 0
+    assert lib.lz77_gpu_segment_size(65535, 255) == 1024
 
 
 def test_no_device_fails_loudly(lib):
@@ -145,7 +147,7 @@ def test_merged_shards_equal_single_stream(orc, lib, sb, la):
     from lz77_b200 import synth
     from lz77_b200.sharding import merge_payloads, shard_ranges, split_stream
     block = lib.lz77_gpu_block_size(sb)
-    seg = lib.lz77_gpu_segment_size()
+    seg = lib.lz77_gpu_segment_size(sb, la)
     T = lib.lz77_token_bits(sb, la)
     data = synth.zipf_text(5 * block + 12_345, seed=4).numpy()
     whole, k_whole = orc.blocked_encode(data, sb, la, block, seg)
@@ -174,7 +176,7 @@ def _gloo_worker(rank, world, port, sb, la, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     orc = oracle()
     lib = api.load_library()
-    block, seg = lib.lz77_gpu_block_size(sb), lib.lz77_gpu_segment_size()
+    block, seg = lib.lz77_gpu_block_size(sb), lib.lz77_gpu_segment_size(sb, la)
     T = lib.lz77_token_bits(sb, la)
 
     def encode_fn(shard, sb_, la_):  # stand-in for lz77_b200.encode_tensor (tests only)
@@ -203,7 +205,7 @@ def _gloo_decode_worker(rank, world, port, sb, la, n, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     orc = oracle()
     lib = api.load_library()
-    block, seg = lib.lz77_gpu_block_size(sb), lib.lz77_gpu_segment_size()
+    block, seg = lib.lz77_gpu_block_size(sb), lib.lz77_gpu_segment_size(sb, la)
     T = lib.lz77_token_bits(sb, la)
 
     def t2b(t):
