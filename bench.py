@@ -314,6 +314,12 @@ def run_cli(src_tensor, sb: int, la: int, gpus: int):
             rec[key + "_wall_s"] = best_wall
             rec[key + "_gbs_process"] = n / best_wall / 1e9
             rec[key + "_gbs_codec_loop"] = steady
+        # the same with the output thrown away: what the file system's write path costs
+        for mode, a, key in (("-c", fin, "encode"), ("-d", flz, "decode")):
+            r = subprocess.run([str(exe), mode, "-i", a, "-o", "/dev/null", "-s", str(sb), "-l", str(la),
+                                "-v", *extra], capture_output=True, text=True)
+            m = re.search(r"in ([0-9.]+) s \(([0-9.]+) GB/s", r.stderr)
+            rec[key + "_gbs_codec_loop_to_devnull"] = float(m.group(2)) if (r.returncode == 0 and m) else None
         rec["stream_bytes"] = os.path.getsize(flz)
         rec["roundtrip_exact"] = open(fin, "rb").read() == open(fout, "rb").read()
     return rec

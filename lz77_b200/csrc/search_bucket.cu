@@ -60,6 +60,10 @@ namespace lz77 {
 #endif
 constexpr int kKeyBits = LZ77_KEY_BITS;
 constexpr int kBuckets = 1 << (2 * kKeyBits);
+#ifndef LZ77_BACKWALK
+#define LZ77_BACKWALK 1  // walk a bucket backwards from the position's own slot (0: forwards from
+                         // the bucket start / the window's lower bound)
+#endif
 #ifndef LZ77_LINEAR_SCAN
 #define LZ77_LINEAR_SCAN 128
 #endif
@@ -274,6 +278,10 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
     const unsigned lt_mask = (1u << lane) - 1u;
     const int cnt_col = warp >> 1, cnt_sh = (warp & 1) * 16;
     static_assert(!kSortedGlobal && sizeof(PosT) == 2, "the token loop reads uint16 buckets from shared memory");
+    // the backward candidate walk needs the counter area for its slot table: not with the
+    // fused emit (its token buffers live there), and only for LA <= 16 (the walk's compare)
+    constexpr bool kBackWalk = LZ77_BACKWALK != 0 && kSmallLA && !kFused && kLanes == 32;
+    const uint32_t sslot = smem_u32(cnt);
     const uint32_t sdata = smem_u32(smem);       // shared-window addresses, computed once
     const uint32_t sbstart = smem_u32(bstart);
     const uint32_t ssorted = smem_u32(sorted);
@@ -505,6 +513,18 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
         if (kSortedGlobal) __threadfence_block();
         __syncthreads();
 
+        const int tile_idx = dst0 + hist_al;  // shared-memory index of the tile's first byte
+        if (kBackWalk) {
+            // own index of every tile position in its bucket list; the counters are dead
+            // now and their area holds the table (tile_bytes * 2 bytes)
+            uint16_t *slot_of = reinterpret_cast<uint16_t *>(cnt);
+            for (int e = threadIdx.x; e < bytes; e += kThreads) {
+                const int q = (int)sorted[e];
+                if (q >= tile_idx) slot_of[q - tile_idx] = (uint16_t)e;
+            }
+            __syncthreads();
+        }
+
         // ---- parse: one group of kLanes lanes per segment -------------------
         const long long seg_lo =
             tile_lo + (long long)(warp * kSegsPerWarp + sg) * kSeg;
@@ -550,41 +570,97 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                         }
                     }
                     const int key = pair_key(tgt[0], tgt[0] >> 8);
-                    const int bs = (int)lds16(sbstart + 2u * key);
-                    const int bn = (int)lds16(sbstart + 2u * key + 2u) - bs;
-                    const uint32_t se = ssorted + 2u * bs;  // shared address of the bucket
                     int best_len = 0, best_q = 0;
-                    // candidates: bucket entries in [lo_idx, p0), oldest first; short
-                    // buckets are walked from their start, long ones from the window's
-                    // lower bound
-                    int i = bn <= kLinearScan
-                                ? 0
-                                : group_lower_bound_s<kLanes>(se, bn, lo_idx, sl, gmask, gshift);
-                    for (; i < bn; i += kLanes) {
-                        const int idx = i + sl;
-                        // LA <= 16: the last round of a bucket reads on into the next one (or the
-                        // padding behind the list).  Whatever turns up there is only accepted as
-                        // an in-window position whose bytes really match, and such a position with
-                        // two or more matching bytes is in this bucket anyway; a one-byte match is
-                        // rescanned below.  Saves the bounds predicate in every round.
-                        const int q = (kSmallLA || idx < bn) ? (int)lds16(se + 2u * idx) : 0x7fffffff;
-                        const bool in = q >= lo_idx && q < p0;
-                        if (kSmallLA) {
+                    if (kBackWalk) {
+                        // Candidates are walked BACKWARDS from the position's own place in its
+                        // bucket list (slot table built after the sort): no bucket size, no lower
+                        // bound of the window start, no round spent on entries that have left the
+                        // window.  The oldest of the longest still wins: ties go to the candidate
+                        // seen later, which is the older one.  A round that matches to the maximum
+                        // length in every lane (runs, short periods: the whole window would
+                        // follow) switches to the forward walk from the window's oldest entry,
+                        // which ends at the first maximum-length match.
+                        const int c_lo = (int)lds16(sbstart + 2u * key);
+                        const int c_hi = (int)lds16(sslot + 2u * (uint32_t)(p0 - tile_idx));
+                        int ci = c_hi - 1;
+                        bool fwd = false;
+                        while (true) {
+                            const int idx = ci - sl;
+                            const int q = idx >= c_lo ? (int)lds16(ssorted + 2u * idx) : -1;
+                            const bool in = q >= lo_idx;  // (entries in front of the own one are older)
                             const int l = round_match_len(sdata, q, in, p0, tgt[0], tgt[1], tgt[2], tgt[3],
                                                           max_len);
-                            // nearer than anything this lane has seen: must be longer
-                            if (l > best_len) {
+                            if (l > 0 && l >= best_len) {
                                 best_len = l;
                                 best_q = q;
                             }
-                        } else if (in) {
-                            const int l = match_len_long(sdata, q, p0, tgt, max_len);
-                            if (l > best_len) {
-                                best_len = l;
-                                best_q = q;
+                            ci -= kLanes;
+                            if (__any_sync(gmask, !in)) break;  // left the window (or the bucket)
+                            if (__all_sync(gmask, l >= max_len)) {
+                                fwd = true;
+                                break;
                             }
                         }
-                        if (__any_sync(gmask, best_len >= max_len || q >= p0)) break;
+                        if (fwd) {
+                            int lo = c_lo, hi = c_hi;  // first entry inside the window
+                            while (lo < hi) {
+                                const int mid = (lo + hi) >> 1;
+                                if ((int)lds16(ssorted + 2u * mid) < lo_idx)
+                                    lo = mid + 1;
+                                else
+                                    hi = mid;
+                            }
+                            best_len = 0;
+                            for (int i = lo; i < c_hi; i += kLanes) {
+                                const int idx = i + sl;
+                                const bool in = idx < c_hi;
+                                const int q = in ? (int)lds16(ssorted + 2u * idx) : p0;
+                                const int l = round_match_len(sdata, q, in, p0, tgt[0], tgt[1], tgt[2],
+                                                              tgt[3], max_len);
+                                if (l > best_len) {
+                                    best_len = l;
+                                    best_q = q;
+                                }
+                                if (__any_sync(gmask, best_len >= max_len)) break;
+                            }
+                        }
+                    } else {
+
+                        const int bs = (int)lds16(sbstart + 2u * key);
+                        const int bn = (int)lds16(sbstart + 2u * key + 2u) - bs;
+                        const uint32_t se = ssorted + 2u * bs;  // shared address of the bucket
+                        // candidates: bucket entries in [lo_idx, p0), oldest first; short
+                        // buckets are walked from their start, long ones from the window's
+                        // lower bound
+                        int i = bn <= kLinearScan
+                                    ? 0
+                                    : group_lower_bound_s<kLanes>(se, bn, lo_idx, sl, gmask, gshift);
+                        for (; i < bn; i += kLanes) {
+                            const int idx = i + sl;
+                            // LA <= 16: the last round of a bucket reads on into the next one (or the
+                            // padding behind the list).  Whatever turns up there is only accepted as
+                            // an in-window position whose bytes really match, and such a position with
+                            // two or more matching bytes is in this bucket anyway; a one-byte match is
+                            // rescanned below.  Saves the bounds predicate in every round.
+                            const int q = (kSmallLA || idx < bn) ? (int)lds16(se + 2u * idx) : 0x7fffffff;
+                            const bool in = q >= lo_idx && q < p0;
+                            if (kSmallLA) {
+                                const int l = round_match_len(sdata, q, in, p0, tgt[0], tgt[1], tgt[2], tgt[3],
+                                                              max_len);
+                                // nearer than anything this lane has seen: must be longer
+                                if (l > best_len) {
+                                    best_len = l;
+                                    best_q = q;
+                                }
+                            } else if (in) {
+                                const int l = match_len_long(sdata, q, p0, tgt, max_len);
+                                if (l > best_len) {
+                                    best_len = l;
+                                    best_q = q;
+                                }
+                            }
+                            if (__any_sync(gmask, best_len >= max_len || q >= p0)) break;
+                        }
                     }
                     // (no candidate: length 0 in the top bits, the start is not used)
                     const uint32_t k = __reduce_max_sync(
