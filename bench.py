@@ -298,7 +298,8 @@ def run_cli(src_tensor, sb: int, la: int, gpus: int):
         fin, flz, fout = (os.path.join(d, x) for x in ("in.bin", "out.lz", "back.bin"))
         src_tensor.cpu().numpy().tofile(fin)
         n = os.path.getsize(fin)
-        extra = ["-G", str(gpus)] if gpus > 1 else []
+        # (several GPUs: one piece = the whole file, so that every GPU gets 1/n of it per call)
+        extra = ["-G", str(gpus), "-p", str(max(32, n >> 20))] if gpus > 1 else []
         for mode, a, b, key in (("-c", fin, flz, "encode"), ("-d", flz, fout, "decode")):
             best_wall, steady = None, None
             for _ in range(2):   # the second run has the files in the page cache

@@ -856,6 +856,26 @@ int lz77_mgpu_init(int n_gpus)
         p->cv_done.wait(lk, [&] { return p->pending == 0; });
     }
     g_pool = p;
+    bool init_ok = true;
+    for (int r = 0; r < n_gpus; r++) init_ok = init_ok && p->init_rc[r] == 0;
+    if (init_ok && n_gpus > 1) {
+        // NCCL connects two ranks the first time they talk: do that here (one tiny input that
+        // gives every rank a block), not inside the first real call
+        const long n = (long)n_gpus * 65536L;
+        std::vector<unsigned char> in((size_t)n, 0), out((size_t)lz77_gpu_encode_bound(n, -1, -1) + 64);
+        long n_out = 0;
+        {
+            std::lock_guard<std::mutex> lk(p->m);
+            p->kind = 1, p->in = in.data(), p->n_in = n, p->sb = -1, p->la = -1;
+            p->out = out.data(), p->out_cap = (long)out.size(), p->n_out = 0;
+            p->pending = p->n;
+            p->gen++;
+        }
+        p->cv_job.notify_all();
+        std::unique_lock<std::mutex> lk(p->m);
+        p->cv_done.wait(lk, [&] { return p->pending == 0; });
+        (void)n_out;
+    }
     for (int r = 0; r < n_gpus; r++)
         if (p->init_rc[r]) {
             const int rc = p->init_rc[r];
