@@ -25,10 +25,18 @@
 
 namespace lz77 {
 
-// key = low 7 bits of x[q], low 6 bits of x[q+1]: a perfect hash of the byte pair
-// for ASCII text, an even spread for binary data
-constexpr int kBigB0Bits = 7, kBigB1Bits = 6;
-constexpr int kBigBuckets = 1 << (kBigB0Bits + kBigB1Bits);  // 8192
+// key = the byte pair itself (65536 buckets per block).  Round 1 used the low 7 + 6 bits
+// (8192 buckets): a perfect hash for ASCII text already, but on binary data eight byte pairs
+// shared a bucket -- 64 entries per block of which one in the window really matched, i.e.
+// two or three candidate rounds and a lower-bound search per token where one round does.
+#ifndef LZ77_BIG_KEY0
+#define LZ77_BIG_KEY0 8
+#endif
+#ifndef LZ77_BIG_KEY1
+#define LZ77_BIG_KEY1 8
+#endif
+constexpr int kBigB0Bits = LZ77_BIG_KEY0, kBigB1Bits = LZ77_BIG_KEY1;
+constexpr int kBigBuckets = 1 << (kBigB0Bits + kBigB1Bits);
 
 __device__ __forceinline__ int big_key(uint32_t b0, uint32_t b1)
 {
@@ -96,8 +104,8 @@ __device__ __forceinline__ void radix_pass(uint32_t *dst, int n, uint32_t *cnt, 
 }
 
 // The block is read straight from HBM/L2 (sequentially, once per pass 1): pass 1
-// orders the positions by the low digit x[q+1]&63 and stores them with the high
-// digit x[q]&127 packed above the position, so pass 2 needs no data access.
+// orders the positions by the low digit x[q+1] and stores them with the high
+// digit x[q] packed above the position, so pass 2 needs no data access.
 __global__ void __launch_bounds__(kSortThreads, 2)
 lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_shift,
                        uint32_t *__restrict__ sorted, uint32_t *__restrict__ tmp,
@@ -112,20 +120,14 @@ lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_sh
     const long long blk_lo = (long long)blockIdx.x << block_shift;
     const int nb = (int)min(block_bytes, n - blk_lo);
     const uint8_t *data = in + blk_lo;
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);                 // [32 warps][128 bins]
-    uint32_t *cnt2 = cnt + kSortWarps * (1 << kBigB0Bits);              // [8192] bucket sizes
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem);  // [32 warps][bins of the wider digit]
     uint32_t *my_sorted = sorted + blk_lo;
     uint32_t *my_tmp = tmp + blk_lo;
     uint32_t *my_bstart = bstart + (long long)blockIdx.x * (kBigBuckets + 1);
     // byte q+1 of the last position of the input does not exist: it reads as 0
     auto byte_at = [&](int q) -> uint32_t { return blk_lo + q < n ? (uint32_t)data[q] : 0u; };
 
-    for (int i = threadIdx.x; i < kBigBuckets; i += kSortThreads) cnt2[i] = 0u;
-    __syncthreads();
-    // bucket sizes (for the bucket start table)
-    for (int i = threadIdx.x; i < nb; i += kSortThreads)
-        atomicAdd(&cnt2[big_key(byte_at(i), byte_at(i + 1))], 1u);
-    // pass 1: low digit = x[q+1] & 63, entries leave as q | (x[q] & 127) << 19
+    // pass 1: low digit = x[q+1], entries leave as q | x[q] << 19
     radix_pass<1 << kBigB1Bits>(
         my_tmp, nb, cnt, bin_start, s_warp, &s_total,
         [&](int i) { return (uint32_t)i; },
@@ -137,22 +139,45 @@ lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_sh
         [&](int i) { return my_tmp[i]; },
         [&](uint32_t el) { return (int)(el >> kPosBits); },
         [&](uint32_t el) { return el & kPosMask; });
-    // bucket starts: exclusive scan of the 8192 bucket sizes
-    {
-        constexpr int per = kBigBuckets / kSortThreads;  // 8
-        uint32_t v[per], sum = 0;
-#pragma unroll
-        for (int b = 0; b < per; b++) {
-            v[b] = cnt2[threadIdx.x * per + b];
-            sum += v[b];
+    // bucket starts from the sorted list: bucket k starts at the first entry whose key is
+    // >= k (entry i writes the starts of the keys in (key[i-1], key[i]]; the last entry also
+    // those behind it).  The list was written by this CTA (fence + barrier in radix_pass).
+    auto key_of = [&](int i) -> int {
+        const int q = (int)my_sorted[i];
+        return big_key(byte_at(q), byte_at(q + 1));
+    };
+    if (nb == 0) {
+        for (int k = threadIdx.x; k <= kBigBuckets; k += kSortThreads) my_bstart[k] = 0u;
+        return;
+    }
+    // short runs of empty buckets are written by the entry's thread, long ones (text uses a
+    // fraction of the 65536 pairs) are queued and filled by the whole CTA
+    constexpr int kGapInline = 32, kGapQueue = kBigBuckets / kGapInline + 2;
+    static_assert(kGapQueue * 3 <= kSortWarps * (1 << (kBigB0Bits > kBigB1Bits ? kBigB0Bits : kBigB1Bits)),
+                  "the gap queue lives in the counter area");
+    int *gap_q = reinterpret_cast<int *>(cnt);
+    if (threadIdx.x == 0) s_total = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb; i += kSortThreads) {
+        const int k_hi = key_of(i);
+        const int k_lo = i > 0 ? key_of(i - 1) + 1 : 0;
+        if (k_hi - k_lo < kGapInline) {
+            for (int k = k_lo; k <= k_hi; k++) my_bstart[k] = (uint32_t)i;
+        } else {
+            const int slot = (int)atomicAdd(&s_total, 1u);
+            gap_q[3 * slot] = k_lo, gap_q[3 * slot + 1] = k_hi, gap_q[3 * slot + 2] = i;
         }
-        uint32_t base = block_exclusive_scan_u32<kSortThreads>(sum, s_warp, &s_total);
-#pragma unroll
-        for (int b = 0; b < per; b++) {
-            my_bstart[threadIdx.x * per + b] = base;
-            base += v[b];
+        if (i == nb - 1) {  // behind the last entry: every remaining bucket is empty
+            const int slot = (int)atomicAdd(&s_total, 1u);
+            gap_q[3 * slot] = k_hi + 1, gap_q[3 * slot + 1] = kBigBuckets, gap_q[3 * slot + 2] = nb;
         }
-        if (threadIdx.x == kSortThreads - 1) my_bstart[kBigBuckets] = base;
+    }
+    __syncthreads();
+    const int n_gaps = (int)s_total;
+    for (int g = 0; g < n_gaps; g++) {
+        const int k_lo = gap_q[3 * g], k_hi = gap_q[3 * g + 1];
+        const uint32_t v = (uint32_t)gap_q[3 * g + 2];
+        for (int k = k_lo + (int)threadIdx.x; k <= k_hi; k += kSortThreads) my_bstart[k] = v;
     }
 }
 
@@ -442,7 +467,8 @@ cudaError_t launch_parse_bigwin(const uint8_t *d_in, long long n_in, long long p
     if (rc != cudaSuccess) return rc;
     BigwinStreams &g_bw = *bwp;
     const size_t piece_scratch = bigwin_piece_scratch(n_in < kBigPiece ? n_in : kBigPiece, P);
-    const size_t sort_smem = (size_t)kSortWarps * (1 << kBigB0Bits) * 4 + (size_t)kBigBuckets * 4;
+    constexpr int kWideBins = 1 << (kBigB0Bits > kBigB1Bits ? kBigB0Bits : kBigB1Bits);
+    const size_t sort_smem = (size_t)kSortWarps * kWideBins * 4;
     rc = cudaFuncSetAttribute(lz77_block_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)sort_smem);
     if (rc != cudaSuccess) return rc;
