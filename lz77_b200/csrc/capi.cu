@@ -427,6 +427,9 @@ int lz77_gpu_encode(const unsigned char *in, long n_in, int sb, int la, unsigned
         const bool split_search = P.window <= 8191;
         // the copy streams start after whatever the compute stream still has queued
         StreamDrain drain(g);
+        // (fused pack: the chunks' kernels run on two streams and look back across launches;
+        // their shared state is zeroed here, in front of all of them)
+        if (pl.fused) CK(launch_parse_bucket_fused_reset(n_in, pl.fused, g.stream));
         CK(cudaEventRecord(g.ev[4], g.stream));
         CK(cudaStreamWaitEvent(g.copy_in, g.ev[4], 0));
         CK(cudaStreamWaitEvent(g.copy_out, g.ev[4], 0));

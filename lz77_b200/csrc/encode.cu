@@ -292,8 +292,11 @@ cudaError_t launch_encode_chunk(const uint8_t *d_in_base, long long pre_base, lo
         // 24-bit tokens, small window: search, parse and pack are one kernel (phase 1)
         if (phase == 2) return cudaSuccess;
         if (ev) cudaEventRecord(ev->e[0], st);
+        // (phase 0 = a call of one launch: it resets the look-back state itself; the chunked
+        // host path resets once, ordered in front of all its streams -- capi.cu)
         cudaError_t rc = launch_parse_bucket_fused(d_in_base, lo, n_chunk, pl.n_total, pre, first,
-                                                   slot, P, pl.fused, (uint8_t *)d_out_words,
+                                                   first && phase == 0, slot, P, pl.fused,
+                                                   (uint8_t *)d_out_words,
                                                    pl.total, host_total, st);
         if (ev) {
             cudaEventRecord(ev->e[1], st);

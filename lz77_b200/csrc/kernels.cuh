@@ -52,9 +52,10 @@ int parse_segment_bytes(int window, int la, bool fused_pack);
 // that may run side by side need different ones)
 bool parse_bucket_fused(const Params &P);
 size_t parse_bucket_fused_scratch(long long n_total);
+cudaError_t launch_parse_bucket_fused_reset(long long n_total, void *scratch, cudaStream_t st);
 cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long long n_in,
-                                      long long n_total, long long pre, bool first, int slot,
-                                      const Params &P, void *scratch, uint8_t *d_out,
+                                      long long n_total, long long pre, bool first, bool reset,
+                                      int slot, const Params &P, void *scratch, uint8_t *d_out,
                                       unsigned long long *total, unsigned long long *host_total,
                                       cudaStream_t st);
 

@@ -25,15 +25,17 @@
 
 namespace lz77 {
 
-// key = the byte pair itself (65536 buckets per block).  Round 1 used the low 7 + 6 bits
-// (8192 buckets): a perfect hash for ASCII text already, but on binary data eight byte pairs
-// shared a bucket -- 64 entries per block of which one in the window really matched, i.e.
-// two or three candidate rounds and a lower-bound search per token where one round does.
+// key = low 7 bits of x[q], low 6 bits of x[q+1] (8192 buckets per block): a perfect hash of
+// the byte pair for ASCII text, an even spread for binary data.  Measured with the byte pair
+// itself as the key (8 + 8 bits, 65536 buckets: one candidate round per token on random data
+// instead of two or three and a lower-bound search): 35.8 vs 36.0 ms on 256 MiB -- the parse
+// is bound by the two dependent L2 round trips per token (bucket start, then entries), not by
+// the rounds, so the smaller tables stay.
 #ifndef LZ77_BIG_KEY0
-#define LZ77_BIG_KEY0 8
+#define LZ77_BIG_KEY0 7
 #endif
 #ifndef LZ77_BIG_KEY1
-#define LZ77_BIG_KEY1 8
+#define LZ77_BIG_KEY1 6
 #endif
 constexpr int kBigB0Bits = LZ77_BIG_KEY0, kBigB1Bits = LZ77_BIG_KEY1;
 constexpr int kBigBuckets = 1 << (kBigB0Bits + kBigB1Bits);

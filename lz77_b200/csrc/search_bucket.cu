@@ -802,9 +802,11 @@ size_t parse_bucket_fused_scratch(long long n_total)
 {
     const long long tile_bytes = (long long)LZ77_PARSE_WARPS * kSegBytes;
     const long long n_tiles = (n_total + tile_bytes - 1) / tile_bytes;
+    // (two sets of spill rows and ring slots: the launches of a chunked call alternate
+    // between two streams and may run side by side)
+    const size_t ctas = (size_t)(n_tiles < kFusedGridMax ? (n_tiles > 0 ? n_tiles : 1) : kFusedGridMax);
     return fused_status_bytes(n_tiles) + (size_t)kMaxTickets * 4 + 256 +
-           (size_t)kFusedGridMax * LZ77_PARSE_WARPS * kTokSpill * 4 +
-           (size_t)kFusedGridMax * kRing * kRingSlot + 1024;
+           2 * (ctas * LZ77_PARSE_WARPS * kTokSpill * 4 + ctas * kRing * kRingSlot) + 1024;
 }
 
 // Bytes after which the greedy parse restarts: part of the stream's specification
@@ -841,12 +843,23 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long p
     return cudaGetLastError();
 }
 
+// Zeroes the look-back words and the tickets of a call over n_total bytes.  Launches of one
+// call may run on several streams: the caller orders this in front of all of them.
+cudaError_t launch_parse_bucket_fused_reset(long long n_total, void *scratch, cudaStream_t st)
+{
+    const long long tile_bytes = (long long)LZ77_PARSE_WARPS * kSegBytes;
+    const long long n_tiles_total = (n_total + tile_bytes - 1) / tile_bytes;
+    return cudaMemsetAsync(scratch, 0, fused_status_bytes(n_tiles_total) + (size_t)kMaxTickets * 4, st);
+}
+
 // The fused path: search + parse + pack in one persistent kernel.  `scratch` as sized by
-// parse_bucket_fused_scratch() for the whole call; `first` zeroes the look-back state
-// (every later chunk of the call continues behind it); slot = the ticket of this launch.
+// parse_bucket_fused_scratch() for the whole call; `first`: the launch that holds the start
+// of the input (writes the header); `reset`: zero the look-back state first (single-launch
+// calls; chunked calls reset once, in front of all their streams); slot = the ticket of
+// this launch.
 cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long long n_in,
-                                      long long n_total, long long pre, bool first, int slot,
-                                      const Params &P, void *scratch, uint8_t *d_out,
+                                      long long n_total, long long pre, bool first, bool reset,
+                                      int slot, const Params &P, void *scratch, uint8_t *d_out,
                                       unsigned long long *total, unsigned long long *host_total,
                                       cudaStream_t st)
 {
@@ -861,12 +874,17 @@ cudaError_t launch_parse_bucket_fused(const uint8_t *d_in, long long lo, long lo
     p += fused_status_bytes(n_tiles_total);
     unsigned int *tickets = (unsigned int *)p;
     p += (size_t)kMaxTickets * 4 + 256;
+    const size_t ctas = (size_t)(n_tiles_total < kFusedGridMax ? (n_tiles_total > 0 ? n_tiles_total : 1)
+                                                               : kFusedGridMax);
+    const size_t spill_bytes = ctas * kW * kTokSpill * 4;
+    const size_t ring_bytes = ctas * kRing * kRingSlot;
+    p += (size_t)(slot & 1) * (spill_bytes + ring_bytes);  // the set of this launch's stream
     uint32_t *spill = (uint32_t *)p;
-    p += (size_t)kFusedGridMax * kW * kTokSpill * 4;
+    p += spill_bytes;
     uint8_t *ring = (uint8_t *)p;
     cudaError_t rc;
-    if (first) {
-        rc = cudaMemsetAsync(scratch, 0, fused_status_bytes(n_tiles_total) + (size_t)kMaxTickets * 4, st);
+    if (reset) {
+        rc = launch_parse_bucket_fused_reset(n_total, scratch, st);
         if (rc != cudaSuccess) return rc;
     }
     if (slot < 0 || slot >= kMaxTickets) return cudaErrorInvalidValue;

@@ -6,9 +6,13 @@ device, stream size == header + tokens * T, decode_size == n).
 
     python tools/run_configs.py [--quick]
 
-configs[3] (4 GiB over 4 GPUs) and configs[4] (32 GiB over 8 GPUs) shard whole
-blocks across ranks with no data-path collective, so one GPU's share (1 GiB /
-4 GiB of the same generator) is what a rank executes.
+configs[3] (4 GiB over 4 GPUs) and configs[4] (32 GiB over 8 GPUs) are sharded runs of
+whole blocks: here one GPU's share (1 GiB / 4 GiB of the same generator), i.e. what a rank
+executes; the sharded one-stream runs themselves are `bench.py --gpus 4|8` (`sharded`
+record).  Every line also carries the history-mode figures (window across block seams,
+pointer-jumping decode) and `ref_decoder_ok`: the first 8 MiB of the stream decoded by the
+compiled reference (`oracle/_ref/lz77 -d`; the full first / middle / last 64 MiB check is
+tests/test_gpu_parity_at_size.py).
 """
 import argparse
 import json
@@ -75,9 +79,31 @@ def main():
         ok = bool(torch.equal(back, src)) and c == 4 + (k * T + 7) // 8 and \
             api.decode_size_tensor(s) == n
         copy_ms = t_dec["dec_copy_ms"]
+        # an independent decoder on a block-aligned cut of the stream
+        ref_ok = None
+        try:
+            from oracle import ref_binary, ref_run
+            if ref_binary() is not None:
+                cut = min(n, 8 << 20) // lz77_b200.block_size(sb) * lz77_b200.block_size(sb)
+                if cut > 0:
+                    k_hi, p_hi = lz77_b200.token_at_tensor(s, cut)
+                    part = lz77_b200.slice_tokens_tensor(s, 0, k_hi).cpu().numpy().tobytes()
+                    ref_ok = p_hi == cut and ref_run("-d", part) == src[:cut].cpu().numpy().tobytes()
+        except Exception as exc:  # noqa: BLE001
+            ref_ok = f"failed: {exc}"
+        # history mode: the reference's sliding window, pointer-jumping decode
+        api.set_history(True)
+        t0 = time.perf_counter()
+        hs, hk = api.encode_tensor(src, la=la, sb=sb, out=stream_buf)
+        t1 = time.perf_counter()
+        hback = api.decode_tensor(hs, out=out_buf)
+        t2 = time.perf_counter()
+        api.set_history(False)
+        hist = {"ratio": n / hs.numel(), "encode_gbs": n / (t1 - t0) / 1e9,
+                "jump_decode_gbs": n / (t2 - t1) / 1e9, "roundtrip_bit_exact": bool(torch.equal(hback, src))}
         line = {
             "config": name, "bytes": n, "sb": sb, "la": la, "token_bits": T, "tokens": k,
-            "ratio": n / c, "roundtrip_bit_exact": ok,
+            "ratio": n / c, "roundtrip_bit_exact": ok, "ref_decoder_ok": ref_ok, "history_mode": hist,
             "encode_gbs": n / best_enc / 1e9, "decode_gbs": n / best_dec / 1e9,
             "kernel_ms": {"search": t_enc["enc_search_ms"], "pack": t_enc["enc_pack_ms"],
                           "dec_scan": t_dec["dec_scan_ms"], "dec_copy": copy_ms},
