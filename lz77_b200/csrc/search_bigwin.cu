@@ -394,7 +394,10 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, long long 
 
 // ---------------------------------------------------------------------------
 
-constexpr long long kBigPiece = 64ll << 20;  // bucket tables are built for this much input at a time
+#ifndef LZ77_BIG_PIECE_MIB
+#define LZ77_BIG_PIECE_MIB 64
+#endif
+constexpr long long kBigPiece = (long long)LZ77_BIG_PIECE_MIB << 20;  // bucket tables are built for this much input at a time
 
 static size_t bigwin_piece_scratch(long long n_in, const Params &P)
 {
