@@ -51,8 +51,11 @@ def csrc_sha16() -> str:
     reported while they describe the kernels that are actually running."""
     import hashlib
     h = hashlib.sha256()
-    for f in sorted((ROOT / "lz77_b200" / "csrc").glob("*.cu*")):
-        h.update(f.name.encode())
+    # the files that hold the codec kernels (capi.cu / comm.cu / context.cuh are host code)
+    for name in ("common.cuh", "kernels.cuh", "match.cuh", "search_bucket.cu", "search_bigwin.cu",
+                 "encode.cu", "decode.cu", "decode_jump.cu"):
+        f = ROOT / "lz77_b200" / "csrc" / name
+        h.update(name.encode())
         h.update(f.read_bytes())
     return h.hexdigest()[:16]
 

@@ -254,6 +254,7 @@ int create_context(Context &c, int device)
 // Destroys every context of the process.  No other thread may be inside the library.
 void lz77_gpu_shutdown(void)
 {
+    lz77_mgpu_shutdown();  // the worker threads of the single-process pool use these contexts
     std::lock_guard<std::mutex> lock(g_init_mutex);
     for (int d = 0; d < kMaxDevices; d++) destroy_context(g_ctx[d]);
     g_default.store(nullptr, std::memory_order_release);
