@@ -667,7 +667,9 @@ def run_native(args):
                          "frac": search_gbs / peak,
                          "traffic": ncu_figure("lz77_parse_bucket_kernel", n),
                          "peak_source": peak_src,
-                         "algorithmic_bytes": alg_bytes},
+                         "algorithmic_bytes": alg_bytes,
+                         "issue_bound": issue_bound("lz77_parse_bucket_kernel", n, k,
+                                                    med["enc_search_ms"], clocks)},
             "roofline_decode": {"kernel": "lz77_decode_tile_kernel (match copy)",
                                 "bound": "hbm", "achieved": copy_gbs, "peak": peak,
                                 "unit": "GB/s", "frac": copy_gbs / peak,
