@@ -187,8 +187,11 @@ lz77_decode_scan_kernel(const uint32_t *__restrict__ words, long long n_words, l
 // stride 48 bytes, or 80 with padding: conflict-free per quarter warp).  The per-token
 // work left -- tile table, block-containment check -- only runs in the few threads whose
 // run touches a tile boundary or the first `window` bytes of a block.
+#ifndef LZ77_DS_MINBLOCKS
+#define LZ77_DS_MINBLOCKS 8
+#endif
 template <int kT>
-__global__ void __launch_bounds__(kDsThreads)
+__global__ void __launch_bounds__(kDsThreads, LZ77_DS_MINBLOCKS)
 lz77_decode_scan_fast_kernel(const uint32_t *__restrict__ words, long long n_words,
                              long long n_tokens, Params P, int tile_shift,
                              unsigned long long *status, long long *__restrict__ tile_tok,
@@ -228,18 +231,17 @@ lz77_decode_scan_fast_kernel(const uint32_t *__restrict__ words, long long n_wor
     }
     const uint32_t len_mask = (1u << P.lb) - 1u, off_mask = (1u << P.ob) - 1u;
     const long long k_first = tok0 + (long long)threadIdx.x * kPer;
-    uint32_t tok[kPer];
+    // token i of the run, from the words in registers (recomputed where it is needed again:
+    // keeping all 16 alive costs the registers of two more resident CTAs per SM)
+    auto token = [&](int i) -> uint32_t {
+        if (kT == 32) return wv[i];
+        const int b = 3 * i;
+        return __funnelshift_r(wv[b >> 2], wv[(b >> 2) + 1], (b & 3) * 8) & 0xffffffu;
+    };
     uint32_t sum = 0;
 #pragma unroll
-    for (int i = 0; i < kPer; i++) {
-        if (kT == 32) {
-            tok[i] = wv[i];
-        } else {
-            const int b = 3 * i;
-            tok[i] = __funnelshift_r(wv[b >> 2], wv[(b >> 2) + 1], (b & 3) * 8) & 0xffffffu;
-        }
-        if (k_first + i < n_tokens) sum += ((tok[i] >> P.ob) & len_mask) + 1u;
-    }
+    for (int i = 0; i < kPer; i++)
+        if (k_first + i < n_tokens) sum += ((token(i) >> P.ob) & len_mask) + 1u;
     // exclusive prefix of the thread sums inside the CTA
     uint32_t inc = sum;
 #pragma unroll
@@ -299,9 +301,10 @@ lz77_decode_scan_fast_kernel(const uint32_t *__restrict__ words, long long n_wor
 #pragma unroll
     for (int i = 0; i < kPer; i++) {
         if (k_first + i >= n_tokens) break;
-        const uint32_t len = (tok[i] >> P.ob) & len_mask;
+        const uint32_t tk = token(i);
+        const uint32_t len = (tk >> P.ob) & len_mask;
         const long long Lr = (long long)len + 1;
-        if (len > 0 && (long long)(tok[i] & off_mask) > (pos & (P.block - 1))) info->cross_block = 1u;
+        if (len > 0 && (long long)(tk & off_mask) > (pos & (P.block - 1))) info->cross_block = 1u;
         const long long j = (pos + tile_bytes - 1) >> tile_shift;
         if ((j << tile_shift) < pos + Lr) {
             tile_tok[j] = k_first + i;
