@@ -67,6 +67,10 @@ constexpr int kBuckets = 1 << (2 * kKeyBits);
 #ifndef LZ77_LINEAR_SCAN
 #define LZ77_LINEAR_SCAN 128
 #endif
+#ifndef LZ77_TOKLOOP
+#define LZ77_TOKLOOP 2  // 2: token loop written against the ALU pipe (packed running best, uniform
+                        // loop control); 1: the round-1 loop
+#endif
 constexpr int kLinearScan = LZ77_LINEAR_SCAN;  // buckets up to this size are scanned from their start
 
 __device__ __forceinline__ int pair_key(uint32_t b0, uint32_t b1)
@@ -180,6 +184,41 @@ __device__ __forceinline__ int round_match_len(uint32_t sdata, int q, bool in, i
     return in ? min(l, max_len) : 0;
 }
 
+// The same compare for the packed-key token loop (LZ77_TOKLOOP 2): no select in front of the
+// loads -- a lane without a candidate carries q = 0, reads the first staged bytes and is
+// masked by the caller -- and no clamp of the first level (every lane whose first word
+// matches is overwritten by the deeper levels).  The result is unspecified when `in` is false.
+__device__ __forceinline__ int cand_match_len(uint32_t sdata, int q, bool in, int p0, uint32_t tgt0,
+                                              uint32_t tgt1)
+{
+    const uint32_t w = sdata + (uint32_t)(q & ~3);
+    const int sh = (q & 3) * 8;
+    const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
+    uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt0;
+    int l = (__ffs(x) - 1) >> 3;
+    if (in && x == 0u) {
+        const uint32_t a2 = lds32(w + 8);
+        x = __funnelshift_r(a1, a2, sh) ^ tgt1;
+        if (x) {
+            l = 4 + ((__ffs(x) - 1) >> 3);
+        } else {
+            const uint32_t pw = sdata + (uint32_t)(p0 & ~3);
+            const int psh = (p0 & 3) * 8;
+            const uint32_t t2 = lds32(pw + 8), t3 = lds32(pw + 12), t4 = lds32(pw + 16);
+            const uint32_t a3 = lds32(w + 12);
+            x = __funnelshift_r(a2, a3, sh) ^ __funnelshift_r(t2, t3, psh);
+            if (x) {
+                l = 8 + ((__ffs(x) - 1) >> 3);
+            } else {
+                const uint32_t a4 = lds32(w + 16);
+                x = __funnelshift_r(a3, a4, sh) ^ __funnelshift_r(t3, t4, psh);
+                l = x ? 12 + ((__ffs(x) - 1) >> 3) : 16;
+            }
+        }
+    }
+    return l;
+}
+
 // first index in [0, n) of the ascending uint16 list at shared address se whose
 // value is >= lo (n if none); uniform across the kLanes lanes of a group
 template <int kLanes>
@@ -274,7 +313,10 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                                  : reinterpret_cast<PosT *>(cnt + kCntWords);
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    // (through REDUX: the compiler then knows the warp index -- and the segment bounds and
+    // the parse position derived from it -- to be uniform and keeps them off the vector ALU)
+    const int warp = LZ77_TOKLOOP == 2 ? (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5)
+                                       : (int)(threadIdx.x >> 5);
     const unsigned lt_mask = (1u << lane) - 1u;
     const int cnt_col = warp >> 1, cnt_sh = (warp & 1) * 16;
     static_assert(!kSortedGlobal && sizeof(PosT) == 2, "the token loop reads uint16 buckets from shared memory");
@@ -546,7 +588,118 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                                         : nullptr;
             int ntok_f = 0;
 
-            while (p0 < seg_end) {
+
+            if constexpr (kBackWalk && LZ77_TOKLOOP == 2) {
+                // ---- token loop written against the ALU pipe (ncu: the vector ALU is the
+                // busiest unit of this kernel, 76 % of its cycles, the FMA pipe idles) ----
+                // The running best of a lane is ONE packed key, len * 65536 - start: a single
+                // multiply-add (FMA pipe) and a max per round replace two compares and two
+                // selects, equal lengths prefer the older start for free, and the REDUX result
+                // unpacks on the uniform datapath together with the loop control.  The last
+                // byte of a segment (no match possible, tree.c:136) leaves the loop, so no
+                // test of the lookahead length per token; a position without reach finds no
+                // candidate inside its window and falls through as a literal.
+                constexpr int kNone = -65535;  // length 0, no start
+                const int la1 = la - 1;
+                const int last = seg_end - 1;
+                int ntok = 0;
+                while (p0 < last) {
+                    const int max_len = min(la1, last - p0);          // lz77.c:87,134 + tree.c:136
+                    const int lo_idx = max(p0 - window, first_idx);   // lz77.c:101-105
+                    const uint32_t w = sdata + (uint32_t)(p0 & ~3);
+                    const int sh = (p0 & 3) * 8;
+                    const uint32_t a0 = lds32(w), a1 = lds32(w + 4), a2 = lds32(w + 8);
+                    const uint32_t tgt0 = __funnelshift_r(a0, a1, sh);
+                    const uint32_t tgt1 = __funnelshift_r(a1, a2, sh);
+                    const int key = pair_key(tgt0, tgt0 >> 8);
+                    const int c_lo = (int)lds16(sbstart + 2u * key);
+                    const int c_hi = (int)lds16(sslot + 2u * (uint32_t)(p0 - tile_idx));
+                    int best = kNone;
+                    int ci = c_hi - 1 - lane;
+                    bool fwd = false;
+                    while (true) {
+                        const int q = ci >= c_lo ? (int)lds16(ssorted + 2u * ci) : 0;
+                        const bool in = q >= lo_idx;  // (q = 0 lies in front of every window)
+                        const int l = min(cand_match_len(sdata, q, in, p0, tgt0, tgt1), max_len);
+                        const int k = l * 65536 - q;
+                        best = max(best, in ? k : kNone);
+                        ci -= 32;
+                        if (__any_sync(0xffffffffu, !in)) break;  // left the window (or the bucket)
+                        if (__all_sync(0xffffffffu, l >= max_len)) {
+                            fwd = true;
+                            break;
+                        }
+                    }
+                    if (fwd) {
+                        // every candidate of a full round matched to the maximum (runs, short
+                        // periods): the oldest such entry of the window ends the search
+                        int lo = c_lo, hi = c_hi;  // first entry inside the window
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if ((int)lds16(ssorted + 2u * mid) < lo_idx)
+                                lo = mid + 1;
+                            else
+                                hi = mid;
+                        }
+                        best = kNone;
+                        for (int i = lo; i < c_hi; i += 32) {
+                            const int idx = i + lane;
+                            const bool in = idx < c_hi;
+                            const int q = in ? (int)lds16(ssorted + 2u * idx) : 0;
+                            const int l = min(cand_match_len(sdata, q, in, p0, tgt0, tgt1), max_len);
+                            best = max(best, in ? l * 65536 - q : kNone);
+                            if (__any_sync(0xffffffffu, best >= max_len * 65536 - 65535)) break;
+                        }
+                    }
+                    const int kbest = __reduce_max_sync(0xffffffffu, best);
+                    int len = (kbest + 65535) >> 16;
+                    int q_best = (len << 16) - kbest;
+                    if (len < 2) {
+                        // length 1: the oldest byte of the window equal to the first
+                        // lookahead byte -- forward SWAR scan of the staged window, 512
+                        // bytes per step (such bytes sit in many buckets)
+                        const uint32_t b0x4 = (tgt0 & 0xffu) * 0x01010101u;
+                        int q1 = 0x7fffffff;
+                        for (int base = lo_idx & ~15; base < p0; base += 512) {
+                            const int g = base + lane * 16;
+                            if (g < p0) {
+                                const uint32_t ga = sdata + (uint32_t)g;
+                                uint32_t wv[4];
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3])
+                                             : "r"(ga));
+#pragma unroll
+                                for (int wi = 3; wi >= 0; wi--) {
+                                    uint32_t m = zero_bytes(wv[wi] ^ b0x4);
+                                    while (m) {
+                                        const int bit = __ffs(m) - 1;
+                                        m ^= 1u << bit;
+                                        const int q = g + 4 * wi + (bit >> 3);
+                                        if (q >= lo_idx && q < p0 && q < q1) q1 = q;
+                                    }
+                                }
+                            }
+                            if (__any_sync(0xffffffffu, q1 != 0x7fffffff)) break;
+                        }
+                        q1 = (int)__reduce_min_sync(0xffffffffu, (unsigned)q1);
+                        len = q1 != 0x7fffffff ? 1 : 0;
+                        q_best = q1;
+                    }
+                    const uint32_t off = len ? (uint32_t)(p0 - q_best) : 0u;
+                    const uint32_t lit = lds8(sdata + (uint32_t)(p0 + len));
+                    const uint32_t tok = off | ((uint32_t)len << len_shift) | (lit << lit_shift);
+                    if (lane == 0) tok_row[ntok] = tok;
+                    ntok++;
+                    p0 += len + 1;
+                }
+                if (p0 == last) {  // the segment's last byte: a literal
+                    if (lane == 0) tok_row[ntok] = lds8(sdata + (uint32_t)p0) << lit_shift;
+                    ntok++;
+                    p0++;
+                }
+                tok_at = tok_row + ntok;
+            }
+            while (!(kBackWalk && LZ77_TOKLOOP == 2) && p0 < seg_end) {
                 const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
                 const int reach = min(p0 - first_idx, window);  // lz77.c:101-105
                 int len = 0, off = 0;
