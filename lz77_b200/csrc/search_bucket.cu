@@ -37,6 +37,9 @@
 //     tokens to scratch, count scan, lz77_pack_kernel (encode.cu).
 #include "kernels.cuh"
 #include "match.cuh"
+#ifdef LZ77_DEBUG_WALK
+#include <cstdio>
+#endif
 
 namespace lz77 {
 
@@ -66,6 +69,10 @@ constexpr int kBuckets = 1 << (2 * kKeyBits);
 #endif
 #ifndef LZ77_LINEAR_SCAN
 #define LZ77_LINEAR_SCAN 128
+#endif
+#ifndef LZ77_SENTINEL
+#define LZ77_SENTINEL 1  // (token loop 2) a zero entry in front of every bucket list ends the backward
+                         // walk: no bucket start per token, no bounds test per round, no bstart array
 #endif
 #ifndef LZ77_TOKLOOP
 #define LZ77_TOKLOOP 2  // 2: token loop written against the ALU pipe (packed running best, uniform
@@ -192,7 +199,7 @@ __device__ __forceinline__ int cand_match_len(uint32_t sdata, int q, bool in, in
                                               uint32_t tgt1)
 {
     const uint32_t w = sdata + (uint32_t)(q & ~3);
-    const int sh = (q & 3) * 8;
+    const int sh = q * 8;  // (the funnel shift wraps: only bits 3..4 count)
     const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
     uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt0;
     int l = (__ffs(x) - 1) >> 3;
@@ -203,7 +210,7 @@ __device__ __forceinline__ int cand_match_len(uint32_t sdata, int q, bool in, in
             l = 4 + ((__ffs(x) - 1) >> 3);
         } else {
             const uint32_t pw = sdata + (uint32_t)(p0 & ~3);
-            const int psh = (p0 & 3) * 8;
+            const int psh = p0 * 8;
             const uint32_t t2 = lds32(pw + 8), t3 = lds32(pw + 12), t4 = lds32(pw + 16);
             const uint32_t a3 = lds32(w + 12);
             x = __funnelshift_r(a2, a3, sh) ^ __funnelshift_r(t2, t3, psh);
@@ -306,11 +313,18 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
     constexpr int kCntWords = kBuckets * (kWarps / 2);  // two 16-bit counters per word
     constexpr int tile_bytes = kWarps * kSegsPerWarp * kSeg;
     const int data_cap = hist_cap + tile_bytes + 64;
+    // the backward candidate walk needs the counter area for its slot table: not with the
+    // fused emit (its token buffers live there), and only for LA <= 16 (the walk's compare)
+    constexpr bool kBackWalk = LZ77_BACKWALK != 0 && kSmallLA && !kFused && kLanes == 32;
+    // sentinel layout: [32 zero entries][bucket 0: sentinel 0, entries][bucket 1: ...]; the
+    // bucket starts only exist folded into the scatter's counters, there is no bstart array
+    constexpr bool kSent = kBackWalk && LZ77_TOKLOOP == 2 && LZ77_SENTINEL != 0;
     PosT *bstart = reinterpret_cast<PosT *>(smem + ((data_cap + 15) & ~15));
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bstart) +
-                                                 (((kBuckets + 1) * sizeof(PosT) + 15) & ~15));
+    uint32_t *cnt = kSent ? reinterpret_cast<uint32_t *>(bstart)
+                          : reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bstart) +
+                                                         (((kBuckets + 1) * sizeof(PosT) + 15) & ~15));
     PosT *sorted = kSortedGlobal ? sorted_global + (long long)blockIdx.x * sorted_stride
-                                 : reinterpret_cast<PosT *>(cnt + kCntWords);
+                                 : reinterpret_cast<PosT *>(cnt + kCntWords) + (kSent ? 32 : 0);
 
     const int lane = threadIdx.x & 31;
     // (through REDUX: the compiler then knows the warp index -- and the segment bounds and
@@ -320,9 +334,6 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
     const unsigned lt_mask = (1u << lane) - 1u;
     const int cnt_col = warp >> 1, cnt_sh = (warp & 1) * 16;
     static_assert(!kSortedGlobal && sizeof(PosT) == 2, "the token loop reads uint16 buckets from shared memory");
-    // the backward candidate walk needs the counter area for its slot table: not with the
-    // fused emit (its token buffers live there), and only for LA <= 16 (the walk's compare)
-    constexpr bool kBackWalk = LZ77_BACKWALK != 0 && kSmallLA && !kFused && kLanes == 32;
     const uint32_t sslot = smem_u32(cnt);
     const uint32_t sdata = smem_u32(smem);       // shared-window addresses, computed once
     const uint32_t sbstart = smem_u32(bstart);
@@ -335,6 +346,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
         mbar_init(&mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (kSent && threadIdx.x < 32) (sorted - 32)[threadIdx.x] = (PosT)0;  // the walk's first round may reach here
     __syncthreads();
 
     // ---- fused path: tiles parked in the ring, their place in the stream pending ----
@@ -499,12 +511,26 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                 sum += run;
             }
             uint32_t base = block_exclusive_scan_u32<kThreads>(sum, s_warp, &s_total);
+            if (kSent) {
+                // bucket k: sentinel at base + k, entries behind it; the start is folded into
+                // both halves of the warps' counters, so the scatter reads nothing else
 #pragma unroll
-            for (int b = 0; b < per; b++) {
-                bstart[threadIdx.x * per + b] = (PosT)base;
-                base += tot[b];
+                for (int b = 0; b < per; b++) {
+                    const uint32_t first = base + (uint32_t)(threadIdx.x * per + b) + 1u;
+                    sorted[first - 1u] = (PosT)0;
+                    uint32_t *c = cnt + (threadIdx.x * per + b) * (kWarps / 2);
+#pragma unroll
+                    for (int w = 0; w < kWarps / 2; w++) c[w] += first * 0x10001u;
+                    base += tot[b];
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < per; b++) {
+                    bstart[threadIdx.x * per + b] = (PosT)base;
+                    base += tot[b];
+                }
+                if (threadIdx.x == kThreads - 1) bstart[kBuckets] = (PosT)base;
             }
-            if (threadIdx.x == kThreads - 1) bstart[kBuckets] = (PosT)base;
         }
         __syncthreads();
         // Every lane takes part -- a lane past the end with a key of its own -- because a
@@ -546,7 +572,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                                     (uint32_t)__popc(peers[b]) << cnt_sh);
                 old = __shfl_sync(0xffffffffu, old, leader);
                 if (valid) {
-                    const int slot = (int)bstart[key[b]] + (int)((old >> cnt_sh) & 0xffffu) +
+                    const int slot = (kSent ? 0 : (int)bstart[key[b]]) + (int)((old >> cnt_sh) & 0xffffu) +
                                      __popc(peers[b] & lt_mask);
                     sorted[slot] = (PosT)i;
                 }
@@ -560,8 +586,8 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
             // own index of every tile position in its bucket list; the counters are dead
             // now and their area holds the table (tile_bytes * 2 bytes)
             uint16_t *slot_of = reinterpret_cast<uint16_t *>(cnt);
-            for (int e = threadIdx.x; e < bytes; e += kThreads) {
-                const int q = (int)sorted[e];
+            for (int e = threadIdx.x; e < bytes + (kSent ? kBuckets : 0); e += kThreads) {
+                const int q = (int)sorted[e];  // (a sentinel reads as position 0: in front of the tile)
                 if (q >= tile_idx) slot_of[q - tile_idx] = (uint16_t)e;
             }
             __syncthreads();
@@ -602,24 +628,37 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                 constexpr int kNone = -65535;  // length 0, no start
                 const int la1 = la - 1;
                 const int last = seg_end - 1;
+                uint32_t len_mul = 1u << len_shift, lit_mul = 1u << lit_shift;
+                asm("" : "+r"(len_mul), "+r"(lit_mul));  // (opaque: keeps the multiplies)
                 int ntok = 0;
                 while (p0 < last) {
                     const int max_len = min(la1, last - p0);          // lz77.c:87,134 + tree.c:136
                     const int lo_idx = max(p0 - window, first_idx);   // lz77.c:101-105
                     const uint32_t w = sdata + (uint32_t)(p0 & ~3);
-                    const int sh = (p0 & 3) * 8;
+                    const int sh = p0 * 8;  // (the funnel shift wraps: only bits 3..4 count)
                     const uint32_t a0 = lds32(w), a1 = lds32(w + 4), a2 = lds32(w + 8);
                     const uint32_t tgt0 = __funnelshift_r(a0, a1, sh);
                     const uint32_t tgt1 = __funnelshift_r(a1, a2, sh);
-                    const int key = pair_key(tgt0, tgt0 >> 8);
-                    const int c_lo = (int)lds16(sbstart + 2u * key);
                     const int c_hi = (int)lds16(sslot + 2u * (uint32_t)(p0 - tile_idx));
+                    int c_lo = 0;
+                    if (!kSent) c_lo = (int)lds16(sbstart + 2u * pair_key(tgt0, tgt0 >> 8));
                     int best = kNone;
                     int ci = c_hi - 1 - lane;
                     bool fwd = false;
                     while (true) {
-                        const int q = ci >= c_lo ? (int)lds16(ssorted + 2u * ci) : 0;
+                        // sentinel layout: the zero entry in front of the bucket ends the walk
+                        // like an entry that has left the window; lanes beyond it read entries
+                        // of other buckets, which differ within the first two bytes -- a length
+                        // below 2 never reaches the token (the scan below decides those)
+                        const int q = (kSent || ci >= c_lo) ? (int)lds16(ssorted + 2u * ci) : 0;
                         const bool in = q >= lo_idx;  // (q = 0 lies in front of every window)
+#ifdef LZ77_DEBUG_WALK
+                        if (q >= data_cap) {
+                            printf("blk %d warp %d lane %d p0 %d tile_idx %d c_hi %d ci %d q %d lo_idx %d bytes %d\n",
+                                   (int)blockIdx.x, warp, lane, p0, tile_idx, c_hi, ci, q, lo_idx, bytes);
+                            __trap();
+                        }
+#endif
                         const int l = min(cand_match_len(sdata, q, in, p0, tgt0, tgt1), max_len);
                         const int k = l * 65536 - q;
                         best = max(best, in ? k : kNone);
@@ -633,10 +672,16 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                     if (fwd) {
                         // every candidate of a full round matched to the maximum (runs, short
                         // periods): the oldest such entry of the window ends the search
-                        int lo = c_lo, hi = c_hi;  // first entry inside the window
+                        // first entry inside the window.  Sentinel layout: entries are distinct
+                        // ascending positions, so it is not more than `reach` places in front of
+                        // the own one; a probe that lands in another bucket (or on the sentinel)
+                        // fails the key test and counts as "in front of the window"
+                        int lo = kSent ? max(c_hi - (p0 - lo_idx), 0) : c_lo, hi = c_hi;
+                        const int key = pair_key(tgt0, tgt0 >> 8);
                         while (lo < hi) {
                             const int mid = (lo + hi) >> 1;
-                            if ((int)lds16(ssorted + 2u * mid) < lo_idx)
+                            const int qm = (int)lds16(ssorted + 2u * mid);
+                            if (qm < lo_idx || (kSent && bucket_key(smem, qm) != key))
                                 lo = mid + 1;
                             else
                                 hi = mid;
@@ -653,7 +698,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                     }
                     const int kbest = __reduce_max_sync(0xffffffffu, best);
                     int len = (kbest + 65535) >> 16;
-                    int q_best = (len << 16) - kbest;
+                    int off = p0 + kbest - (len << 16);  // p0 - start
                     if (len < 2) {
                         // length 1: the oldest byte of the window equal to the first
                         // lookahead byte -- forward SWAR scan of the staged window, 512
@@ -683,11 +728,12 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                         }
                         q1 = (int)__reduce_min_sync(0xffffffffu, (unsigned)q1);
                         len = q1 != 0x7fffffff ? 1 : 0;
-                        q_best = q1;
+                        off = len ? p0 - q1 : 0;
                     }
-                    const uint32_t off = len ? (uint32_t)(p0 - q_best) : 0u;
+                    // the fields do not overlap: two multiply-adds (FMA pipe) instead of
+                    // two shifts and an OR
                     const uint32_t lit = lds8(sdata + (uint32_t)(p0 + len));
-                    const uint32_t tok = off | ((uint32_t)len << len_shift) | (lit << lit_shift);
+                    const uint32_t tok = lit * lit_mul + ((uint32_t)len * len_mul + (uint32_t)off);
                     if (lane == 0) tok_row[ntok] = tok;
                     ntok++;
                     p0 += len + 1;
@@ -977,15 +1023,19 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long p
 {
     constexpr int kW = LZ77_PARSE_WARPS, kL = LZ77_PARSE_LANES;
     const bool small_la = P.la <= 16;
-    const int hist_cap = (P.window + 15) & ~15;
+    // (at least 16: staged position 0 then lies in front of every window -- the token loop's
+    // "no candidate" value -- also for SB = 1, whose usable window is empty)
+    const int hist_cap = P.window > 0 ? (P.window + 15) & ~15 : 16;
     const long long tile_bytes = (long long)kW * (32 / kL) * kSegBytes;
     const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
     if (n_tiles == 0) return cudaSuccess;
     const size_t data_cap = (size_t)hist_cap + (size_t)tile_bytes + 64;
     size_t smem = (data_cap + 15) & ~(size_t)15;               // staged bytes
-    smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // bucket starts
+    const bool sentinel = small_la && kL == 32 && LZ77_BACKWALK != 0 && LZ77_TOKLOOP == 2 && LZ77_SENTINEL != 0;
+    if (!sentinel) smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // bucket starts
     smem += (size_t)kBuckets * (kW / 2) * 4;                   // per-warp counters
     smem += data_cap * sizeof(uint16_t) + 80;                  // sorted positions + one round of padding
+    if (sentinel) smem += (32 + kBuckets) * sizeof(uint16_t);  // front padding + one zero entry per bucket
     auto kern = small_la ? lz77_parse_bucket_kernel<true, kW, kL, uint16_t, false, false, kSegBytes>
                          : lz77_parse_bucket_kernel<false, kW, kL, uint16_t, false, false, kSegBytes>;
     cudaError_t rc =
