@@ -67,6 +67,49 @@ __device__ __forceinline__ uint32_t zero_bytes(uint32_t x)
     return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
 }
 
+// Oldest position q in [lo_idx, p0) of the staged bytes (shared address sdata) whose byte
+// equals b0 = the byte at p0, or -1: the length-1 match of the reference (tree.c:118-152 finds
+// such a byte when nothing longer exists; ties go to the oldest).  Forward
+// SWAR scan by a whole warp, 512 bytes per step; the result is warp-uniform.  The byte at
+// p0 itself is the scan's sentinel (it always matches and nothing behind it is looked at),
+// so only the first 16-byte chunk needs a bounds mask.
+__device__ __forceinline__ int oldest_byte_match(uint32_t sdata, int lo_idx, int p0, uint32_t b0,
+                                                 int lane)
+{
+    const uint32_t b4 = b0 * 0x01010101u;
+    for (int base = lo_idx & ~15; base < p0; base += 512) {
+        const int g = base + lane * 16;
+        uint32_t z0 = 0u, z1 = 0u, z2 = 0u, z3 = 0u;
+        if (g <= p0) {
+            uint32_t w0, w1, w2, w3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                         : "r"(sdata + (uint32_t)g));
+            z0 = zero_bytes(w0 ^ b4), z1 = zero_bytes(w1 ^ b4);
+            z2 = zero_bytes(w2 ^ b4), z3 = zero_bytes(w3 ^ b4);
+            if (g < lo_idx) {  // (one lane of the first step) bytes in front of the window
+                const int k = lo_idx - g;  // 1..15 of them
+                z0 &= k >= 4 ? 0u : 0xffffffffu << (8 * k);
+                z1 &= k >= 8 ? 0u : (k > 4 ? 0xffffffffu << (8 * (k - 4)) : 0xffffffffu);
+                z2 &= k >= 12 ? 0u : (k > 8 ? 0xffffffffu << (8 * (k - 8)) : 0xffffffffu);
+                z3 &= k > 12 ? 0xffffffffu << (8 * (k - 12)) : 0xffffffffu;
+            }
+        }
+        const uint32_t any = z0 | z1 | z2 | z3;
+        if (__any_sync(0xffffffffu, any != 0u)) {
+            unsigned q = 0x7fffffffu;
+            if (any) {
+                const uint32_t zs = z0 ? z0 : z1 ? z1 : z2 ? z2 : z3;
+                const int wo = z0 ? 0 : z1 ? 4 : z2 ? 8 : 12;
+                q = (unsigned)(g + wo + ((__ffs(zs) - 1) >> 3));
+            }
+            q = __reduce_min_sync(0xffffffffu, q);
+            return (int)q < p0 ? (int)q : -1;
+        }
+    }
+    return -1;
+}
+
 // ---- mbarrier / TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)

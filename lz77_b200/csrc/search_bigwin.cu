@@ -229,6 +229,9 @@ __device__ __forceinline__ int round_match_len_big(const uint8_t *smem, int q, b
 }
 
 constexpr int kBigWarps = 16;
+#ifndef LZ77_BIG_TOKLOOP
+#define LZ77_BIG_TOKLOOP 2  // 2: token loop with a packed running best (see search_bucket.cu); 1: round-1 loop
+#endif
 
 template <bool kSmallLA>
 __global__ void __launch_bounds__(kBigWarps * 32, 2)
@@ -242,7 +245,11 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, long long 
 
     constexpr int kThreads = kBigWarps * 32;
     constexpr int tile_bytes = kBigWarps * kSegBytes;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // (through REDUX: known to be uniform, so the segment bounds and the parse position
+    // derived from it stay off the vector ALU)
+    const int warp = LZ77_BIG_TOKLOOP == 2 ? (int)__reduce_max_sync(0xffffffffu, threadIdx.x >> 5)
+                                           : (int)(threadIdx.x >> 5);
     const long long tile_lo = (long long)blockIdx.x * tile_bytes;
     const long long blk_i = tile_lo >> P.block_shift;
     const long long blk_lo = blk_i << P.block_shift;
@@ -296,7 +303,90 @@ lz77_parse_bigwin_kernel(const uint8_t *__restrict__ in, long long n, long long 
     const int len_shift = P.ob, lit_shift = P.ob + P.lb;
     const int la = P.la, window = P.window;
 
-    while (p0 < seg_end) {
+
+    if (LZ77_BIG_TOKLOOP == 2) {
+        // The vector ALU is the busiest unit of the parse kernels (ncu), so the running best of
+        // a lane is ONE packed key, len * 2^17 - start: a multiply-add (FMA pipe) and a max per
+        // round instead of a compare and two selects; equal lengths prefer the older start for
+        // free; the REDUX result unpacks on the uniform datapath together with the loop
+        // control; the token is two multiply-adds.  The last byte of a segment (no match
+        // possible, tree.c:136) leaves the loop; a position without reach finds no candidate
+        // inside its window and falls through as a literal.
+        const uint32_t sdata = smem_u32(smem);
+        constexpr int kMul = 1 << 17;      // staged indices stay below 2^17 (64 KiB + tile)
+        constexpr int kNone = -(kMul - 1);  // length 0, no start
+        const int la1 = la - 1;
+        const int last = seg_end - 1;
+        uint32_t len_mul = 1u << len_shift, lit_mul = 1u << lit_shift;
+        asm("" : "+r"(len_mul), "+r"(lit_mul));  // (opaque: keeps the multiplies)
+        int ntok = 0;
+        while (p0 < last) {
+            const int max_len = min(la1, last - p0);         // lz77.c:87,134 + tree.c:136
+            const int lo_idx = max(p0 - window, first_idx);  // lz77.c:101-105
+            uint32_t tgt[4];
+            {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(smem + (p0 & ~3));
+                const int sh = p0 * 8;  // (the funnel shift wraps: only bits 3..4 count)
+                const uint32_t a0 = w[0], a1 = w[1];
+                const uint32_t a2 = w[2], a3 = w[3], a4 = w[4];
+                tgt[0] = __funnelshift_r(a0, a1, sh);
+                tgt[1] = __funnelshift_r(a1, a2, sh);
+                tgt[2] = __funnelshift_r(a2, a3, sh);
+                tgt[3] = __funnelshift_r(a3, a4, sh);
+            }
+            const uint32_t b0 = tgt[0] & 0xffu;
+            int best = kNone;
+            if (max_len >= 2 && lo_idx < p0) {
+                const int key = big_key(b0, tgt[0] >> 8);
+                const int full_key = max_len * kMul - (kMul - 1);  // any key of maximum length
+                auto scan_list = [&](const uint32_t *list, const uint32_t *starts, int base_idx) {
+                    const int bs = (int)__ldg(starts + key);
+                    const int bn = (int)__ldg(starts + key + 1) - bs;
+                    const uint32_t *e = list + bs;
+                    const int lo_blk = lo_idx - base_idx, p_blk = p0 - base_idx;
+                    int i = bn <= 64 ? 0 : warp_lower_bound_g(e, bn, lo_blk, lane);
+                    for (; i < bn; i += 32) {
+                        const int idx = i + lane;
+                        const int qb = idx < bn ? (int)__ldg(e + idx) : 0x7fffffff;
+                        const bool in = qb >= lo_blk && qb < p_blk;
+                        const int q = in ? qb + base_idx : 0;
+                        const int l = round_match_len_big<kSmallLA>(smem, q, in, p0, tgt, max_len);
+                        best = max(best, in ? l * kMul - q : kNone);
+                        if (__any_sync(0xffffffffu, best >= full_key || qb >= p_blk)) break;
+                    }
+                };
+                // oldest first: the tail of the previous block's list, then this block's
+                // (not needed once a maximum-length match is in: a later one is not longer)
+                bool full = false;
+                if (has_prev && lo_idx < blk_idx) {
+                    scan_list(prev_sorted, prev_bstart, prev_idx);
+                    full = __any_sync(0xffffffffu, best >= full_key);
+                }
+                if (!full) scan_list(blk_sorted, blk_bstart, blk_idx);
+            }
+            const int kbest = __reduce_max_sync(0xffffffffu, best);
+            int len = (kbest + (kMul - 1)) >> 17;
+            int off = p0 + kbest - (len << 17);  // p0 - start
+            if (len < 2) {
+                // length 1 (such bytes sit in many buckets): scan of the staged window
+                const int q1 = oldest_byte_match(sdata, lo_idx, p0, b0, lane);
+                len = q1 >= 0 ? 1 : 0;
+                off = q1 >= 0 ? p0 - q1 : 0;
+            }
+            const uint32_t lit = smem[p0 + len];
+            const uint32_t tok = lit * lit_mul + ((uint32_t)len * len_mul + (uint32_t)off);
+            if (lane == 0) tok_row[ntok] = tok;
+            ntok++;
+            p0 += len + 1;
+        }
+        if (p0 == last) {  // the segment's last byte: a literal
+            if (lane == 0) tok_row[ntok] = (uint32_t)smem[p0] << lit_shift;
+            ntok++;
+            p0++;
+        }
+        tok_at = tok_row + ntok;
+    }
+    while (LZ77_BIG_TOKLOOP != 2 && p0 < seg_end) {
         const int max_len = min(la, seg_end - p0) - 1;  // lz77.c:87,134 + tree.c:136
         const int reach = min(p0 - first_idx, window);  // lz77.c:101-105
         int len = 0, off = 0;

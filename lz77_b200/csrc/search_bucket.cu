@@ -725,35 +725,10 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                     int len = (kbest + 65535) >> 16;
                     int off = p0 + kbest - (len << 16);  // p0 - start
                     if (len < 2) {
-                        // length 1: the oldest byte of the window equal to the first
-                        // lookahead byte -- forward SWAR scan of the staged window, 512
-                        // bytes per step (such bytes sit in many buckets)
-                        const uint32_t b0x4 = (tgt0 & 0xffu) * 0x01010101u;
-                        int q1 = 0x7fffffff;
-                        for (int base = lo_idx & ~15; base < p0; base += 512) {
-                            const int g = base + lane * 16;
-                            if (g < p0) {
-                                const uint32_t ga = sdata + (uint32_t)g;
-                                uint32_t wv[4];
-                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                             : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3])
-                                             : "r"(ga));
-#pragma unroll
-                                for (int wi = 3; wi >= 0; wi--) {
-                                    uint32_t m = zero_bytes(wv[wi] ^ b0x4);
-                                    while (m) {
-                                        const int bit = __ffs(m) - 1;
-                                        m ^= 1u << bit;
-                                        const int q = g + 4 * wi + (bit >> 3);
-                                        if (q >= lo_idx && q < p0 && q < q1) q1 = q;
-                                    }
-                                }
-                            }
-                            if (__any_sync(0xffffffffu, q1 != 0x7fffffff)) break;
-                        }
-                        q1 = (int)__reduce_min_sync(0xffffffffu, (unsigned)q1);
-                        len = q1 != 0x7fffffff ? 1 : 0;
-                        off = len ? p0 - q1 : 0;
+                        // length 1 (such bytes sit in many buckets): scan of the staged window
+                        const int q1 = oldest_byte_match(sdata, lo_idx, p0, tgt0 & 0xffu, lane);
+                        len = q1 >= 0 ? 1 : 0;
+                        off = q1 >= 0 ? p0 - q1 : 0;
                     }
                     // the fields do not overlap: two multiply-adds (FMA pipe) instead of
                     // two shifts and an OR
