@@ -74,10 +74,6 @@ constexpr int kBuckets = 1 << (2 * kKeyBits);
 #define LZ77_SENTINEL 1  // (token loop 2) a zero entry in front of every bucket list ends the backward
                          // walk: no bucket start per token, no bounds test per round, no bstart array
 #endif
-#ifndef LZ77_PRED_LOADS
-#define LZ77_PRED_LOADS 0  // (token loop 2) 1: only lanes in front of the first entry that left the window
-                           // load their candidate (fewer bank conflicts, but the ballot sits in front of the loads: 6.82 vs 6.69 ms)
-#endif
 #ifndef LZ77_TOKLOOP
 #define LZ77_TOKLOOP 2  // 2: token loop written against the ALU pipe (packed running best, uniform
                         // loop control); 1: the round-1 loop
@@ -204,23 +200,9 @@ __device__ __forceinline__ int cand_match_len(uint32_t sdata, int q, bool in, in
 {
     const uint32_t w = sdata + (uint32_t)(q & ~3);
     const int sh = q * 8;  // (the funnel shift wraps: only bits 3..4 count)
-    // lanes without a candidate do not load: their random addresses would cost the round
-    // extra shared-memory wavefronts (bank conflicts), and shared memory is this kernel's
-    // second-busiest unit
-    uint32_t a0 = 0u, a1 = 0u;
-#if !LZ77_PRED_LOADS
-    a0 = lds32(w), a1 = lds32(w + 4);
-#else
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.u32 p, %3, 0;\n"
-        "@p ld.shared.u32 %0, [%2];\n"
-        "@p ld.shared.u32 %1, [%2+4];\n"
-        "}\n"
-        : "+r"(a0), "+r"(a1)
-        : "r"(w), "r"((uint32_t)in));
-#endif
+    // (ballot-predicated loads -- only lanes in front of the first entry that left the window
+    // load -- cost fewer bank conflicts but put the ballot in front of the loads: 6.82 vs 6.69 ms)
+    const uint32_t a0 = lds32(w), a1 = lds32(w + 4);
     uint32_t x = __funnelshift_r(a0, a1, sh) ^ tgt0;
     int l = (__ffs(x) - 1) >> 3;
     if (in && x == 0u) {
@@ -355,7 +337,14 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
     const int cnt_col = warp >> 1, cnt_sh = (warp & 1) * 16;
     static_assert(!kSortedGlobal && sizeof(PosT) == 2, "the token loop reads uint16 buckets from shared memory");
     const uint32_t sslot = smem_u32(cnt);
-    const uint32_t sdata = smem_u32(smem);       // shared-window addresses, computed once
+    uint32_t sdata = smem_u32(smem);             // shared-window addresses, computed once
+    // (opaque: otherwise the compiler re-derives the shared window base from SR_CgaCtaId for
+    // every token -- four instructions, one of them a special-register read, in front of the
+    // token's first loads)
+#ifndef LZ77_OPAQUE_SDATA
+#define LZ77_OPAQUE_SDATA 1
+#endif
+    if (LZ77_TOKLOOP == 2 && LZ77_OPAQUE_SDATA) asm volatile("" : "+r"(sdata));
     const uint32_t sbstart = smem_u32(bstart);
     const uint32_t ssorted = smem_u32(sorted);
     const int sg = lane / kLanes, sl = lane % kLanes;  // group in the warp, lane in the group
@@ -646,9 +635,9 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                 // test of the lookahead length per token; a position without reach finds no
                 // candidate inside its window and falls through as a literal.
                 constexpr int kNone = -65535;  // length 0, no start
+                constexpr int kFar = 1 << 30;  // a start whose key loses against kNone
                 const int la1 = la - 1;
                 const int last = seg_end - 1;
-                const unsigned le_mask = (2u << lane) - 1u;  // this lane and the nearer ones
                 uint32_t len_mul = 1u << len_shift, lit_mul = 1u << lit_shift;
                 asm("" : "+r"(len_mul), "+r"(lit_mul));  // (opaque: keeps the multiplies)
                 int ntok = 0;
@@ -672,11 +661,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                         // of other buckets, which differ within the first two bytes -- a length
                         // below 2 never reaches the token (the scan below decides those)
                         const int q = (kSent || ci >= c_lo) ? (int)lds16(ssorted + 2u * ci) : 0;
-                        // (q = 0 lies in front of every window.)  Lanes hold ever older entries:
-                        // behind the first one that has left the window nothing counts -- older
-                        // entries of the bucket, the sentinel, entries of other buckets
-                        const unsigned out = __ballot_sync(0xffffffffu, q < lo_idx);
-                        const bool in = LZ77_PRED_LOADS ? (out & le_mask) == 0u : q >= lo_idx;
+                        const bool in = q >= lo_idx;  // (q = 0 lies in front of every window)
 #ifdef LZ77_DEBUG_WALK
                         if (q >= data_cap) {
                             printf("blk %d warp %d lane %d p0 %d tile_idx %d c_hi %d ci %d q %d lo_idx %d bytes %d\n",
@@ -684,11 +669,14 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                             __trap();
                         }
 #endif
+                        // (decided in front of the compare, while the predicate is at hand: an
+                        // entry outside the window gets a start that can never win)
+                        const bool left = __any_sync(0xffffffffu, !in);
+                        const int qk = in ? q : kFar;
                         const int l = min(cand_match_len(sdata, q, in, p0, tgt0, tgt1), max_len);
-                        const int k = l * 65536 - q;
-                        best = max(best, in ? k : kNone);
+                        best = max(best, l * 65536 - qk);
                         ci -= 32;
-                        if (out) break;  // left the window (or the bucket)
+                        if (left) break;  // left the window (or the bucket)
                         if (__all_sync(0xffffffffu, l >= max_len)) {
                             fwd = true;
                             break;
