@@ -45,7 +45,10 @@ __device__ __forceinline__ int big_key(uint32_t b0, uint32_t b1)
     return (int)(((b0 & ((1u << kBigB0Bits) - 1u)) << kBigB1Bits) |
                  (b1 & ((1u << kBigB1Bits) - 1u)));
 }
-constexpr int kSortThreads = 1024;
+#ifndef LZ77_SORT_THREADS
+#define LZ77_SORT_THREADS 1024
+#endif
+constexpr int kSortThreads = LZ77_SORT_THREADS;
 constexpr int kSortWarps = kSortThreads / 32;
 
 // ---------------------------------------------------------------------------

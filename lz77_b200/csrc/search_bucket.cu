@@ -37,9 +37,6 @@
 //     tokens to scratch, count scan, lz77_pack_kernel (encode.cu).
 #include "kernels.cuh"
 #include "match.cuh"
-#ifdef LZ77_DEBUG_WALK
-#include <cstdio>
-#endif
 
 namespace lz77 {
 
@@ -70,9 +67,8 @@ constexpr int kBuckets = 1 << (2 * kKeyBits);
 #ifndef LZ77_LINEAR_SCAN
 #define LZ77_LINEAR_SCAN 128
 #endif
-#ifndef LZ77_SENTINEL
-#define LZ77_SENTINEL 1  // (token loop 2) a zero entry in front of every bucket list ends the backward
-                         // walk: no bucket start per token, no bounds test per round, no bstart array
+#ifndef LZ77_DEFER_STORE
+#define LZ77_DEFER_STORE 1  // (token loop 2) store a token one pass later, behind the next token's loads
 #endif
 #ifndef LZ77_TOKLOOP
 #define LZ77_TOKLOOP 2  // 2: token loop written against the ALU pipe (packed running best, uniform
@@ -320,7 +316,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
     constexpr bool kBackWalk = LZ77_BACKWALK != 0 && kSmallLA && !kFused && kLanes == 32;
     // sentinel layout: [32 zero entries][bucket 0: sentinel 0, entries][bucket 1: ...]; the
     // bucket starts only exist folded into the scatter's counters, there is no bstart array
-    constexpr bool kSent = kBackWalk && LZ77_TOKLOOP == 2 && LZ77_SENTINEL != 0;
+    constexpr bool kSent = kBackWalk && LZ77_TOKLOOP == 2;  // (the token loop 2 layout)
     PosT *bstart = reinterpret_cast<PosT *>(smem + ((data_cap + 15) & ~15));
     uint32_t *cnt = kSent ? reinterpret_cast<uint32_t *>(bstart)
                           : reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(bstart) +
@@ -597,7 +593,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
             uint16_t *slot_of = reinterpret_cast<uint16_t *>(cnt);
             for (int e = threadIdx.x; e < bytes + (kSent ? kBuckets : 0); e += kThreads) {
                 const int q = (int)sorted[e];  // (a sentinel reads as position 0: in front of the tile)
-                if (q >= tile_idx) slot_of[q - tile_idx] = (uint16_t)e;
+                if (q >= tile_idx) slot_of[q - tile_idx] = (uint16_t)(kSent ? 2 * e : e);  // (kSent: byte offset)
             }
             __syncthreads();
         }
@@ -640,6 +636,11 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                 const int last = seg_end - 1;
                 uint32_t len_mul = 1u << len_shift, lit_mul = 1u << lit_shift;
                 asm("" : "+r"(len_mul), "+r"(lit_mul));  // (opaque: keeps the multiplies)
+#if LZ77_DEFER_STORE
+                uint32_t pend_lit = 0u, pend_rest = 0u;
+#endif
+                const uint32_t slot_base = sslot - 2u * (uint32_t)tile_idx;   // slot table by staged index
+                const uint32_t lane_base = ssorted - 2u - 2u * (uint32_t)lane;
                 int ntok = 0;
                 while (p0 < last) {
                     const int max_len = min(la1, last - p0);          // lz77.c:87,134 + tree.c:136
@@ -649,33 +650,30 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                     const uint32_t a0 = lds32(w), a1 = lds32(w + 4), a2 = lds32(w + 8);
                     const uint32_t tgt0 = __funnelshift_r(a0, a1, sh);
                     const uint32_t tgt1 = __funnelshift_r(a1, a2, sh);
-                    const int c_hi = (int)lds16(sslot + 2u * (uint32_t)(p0 - tile_idx));
-                    int c_lo = 0;
-                    if (!kSent) c_lo = (int)lds16(sbstart + 2u * pair_key(tgt0, tgt0 >> 8));
+                    // own place in the bucket list, as a byte offset into the sorted array
+                    const uint32_t c_hi2 = lds16(slot_base + 2u * (uint32_t)p0);
+#if LZ77_DEFER_STORE
+                    // the previous token leaves here, behind this token's first loads: its
+                    // literal (a shared-memory load at the end of the last pass) has arrived
+                    if (ntok > 0 && lane == 0) tok_row[ntok - 1] = pend_lit * lit_mul + pend_rest;
+#endif
                     int best = kNone;
-                    int ci = c_hi - 1 - lane;
+                    uint32_t ca = lane_base + c_hi2;  // this lane's entry: own place - 1 - lane
                     bool fwd = false;
                     while (true) {
-                        // sentinel layout: the zero entry in front of the bucket ends the walk
-                        // like an entry that has left the window; lanes beyond it read entries
-                        // of other buckets, which differ within the first two bytes -- a length
-                        // below 2 never reaches the token (the scan below decides those)
-                        const int q = (kSent || ci >= c_lo) ? (int)lds16(ssorted + 2u * ci) : 0;
+                        // the zero entry in front of the bucket ends the walk like an entry that
+                        // has left the window; lanes beyond it read entries of other buckets,
+                        // which differ within the first two bytes -- a length below 2 never
+                        // reaches the token (the scan below decides those)
+                        const int q = (int)lds16(ca);
                         const bool in = q >= lo_idx;  // (q = 0 lies in front of every window)
-#ifdef LZ77_DEBUG_WALK
-                        if (q >= data_cap) {
-                            printf("blk %d warp %d lane %d p0 %d tile_idx %d c_hi %d ci %d q %d lo_idx %d bytes %d\n",
-                                   (int)blockIdx.x, warp, lane, p0, tile_idx, c_hi, ci, q, lo_idx, bytes);
-                            __trap();
-                        }
-#endif
                         // (decided in front of the compare, while the predicate is at hand: an
                         // entry outside the window gets a start that can never win)
                         const bool left = __any_sync(0xffffffffu, !in);
                         const int qk = in ? q : kFar;
                         const int l = min(cand_match_len(sdata, q, in, p0, tgt0, tgt1), max_len);
                         best = max(best, l * 65536 - qk);
-                        ci -= 32;
+                        ca -= 64u;
                         if (left) break;  // left the window (or the bucket)
                         if (__all_sync(0xffffffffu, l >= max_len)) {
                             fwd = true;
@@ -689,12 +687,13 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                         // ascending positions, so it is not more than `reach` places in front of
                         // the own one; a probe that lands in another bucket (or on the sentinel)
                         // fails the key test and counts as "in front of the window"
-                        int lo = kSent ? max(c_hi - (p0 - lo_idx), 0) : c_lo, hi = c_hi;
+                        const int c_hi = (int)(c_hi2 >> 1);
+                        int lo = max(c_hi - (p0 - lo_idx), 0), hi = c_hi;
                         const int key = pair_key(tgt0, tgt0 >> 8);
                         while (lo < hi) {
                             const int mid = (lo + hi) >> 1;
                             const int qm = (int)lds16(ssorted + 2u * mid);
-                            if (qm < lo_idx || (kSent && bucket_key(smem, qm) != key))
+                            if (qm < lo_idx || bucket_key(smem, qm) != key)
                                 lo = mid + 1;
                             else
                                 hi = mid;
@@ -720,12 +719,20 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                     }
                     // the fields do not overlap: two multiply-adds (FMA pipe) instead of
                     // two shifts and an OR
+#if LZ77_DEFER_STORE
+                    pend_lit = lds8(sdata + (uint32_t)(p0 + len));
+                    pend_rest = (uint32_t)len * len_mul + (uint32_t)off;
+#else
                     const uint32_t lit = lds8(sdata + (uint32_t)(p0 + len));
                     const uint32_t tok = lit * lit_mul + ((uint32_t)len * len_mul + (uint32_t)off);
                     if (lane == 0) tok_row[ntok] = tok;
+#endif
                     ntok++;
                     p0 += len + 1;
                 }
+#if LZ77_DEFER_STORE
+                if (ntok > 0 && lane == 0) tok_row[ntok - 1] = pend_lit * lit_mul + pend_rest;
+#endif
                 if (p0 == last) {  // the segment's last byte: a literal
                     if (lane == 0) tok_row[ntok] = lds8(sdata + (uint32_t)p0) << lit_shift;
                     ntok++;
@@ -1019,7 +1026,7 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long p
     if (n_tiles == 0) return cudaSuccess;
     const size_t data_cap = (size_t)hist_cap + (size_t)tile_bytes + 64;
     size_t smem = (data_cap + 15) & ~(size_t)15;               // staged bytes
-    const bool sentinel = small_la && kL == 32 && LZ77_BACKWALK != 0 && LZ77_TOKLOOP == 2 && LZ77_SENTINEL != 0;
+    const bool sentinel = small_la && kL == 32 && LZ77_BACKWALK != 0 && LZ77_TOKLOOP == 2;
     if (!sentinel) smem += ((kBuckets + 1) * sizeof(uint16_t) + 15) & ~(size_t)15;  // bucket starts
     smem += (size_t)kBuckets * (kW / 2) * 4;                   // per-warp counters
     smem += data_cap * sizeof(uint16_t) + 80;                  // sorted positions + one round of padding
