@@ -111,7 +111,10 @@ __device__ __forceinline__ void radix_pass(uint32_t *dst, int n, uint32_t *cnt, 
 // The block is read straight from HBM/L2 (sequentially, once per pass 1): pass 1
 // orders the positions by the low digit x[q+1] and stores them with the high
 // digit x[q] packed above the position, so pass 2 needs no data access.
-__global__ void __launch_bounds__(kSortThreads, 2)
+#ifndef LZ77_SORT_MINBLOCKS
+#define LZ77_SORT_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kSortThreads, LZ77_SORT_MINBLOCKS)
 lz77_block_sort_kernel(const uint8_t *__restrict__ in, long long n, int block_shift,
                        uint32_t *__restrict__ sorted, uint32_t *__restrict__ tmp,
                        uint32_t *__restrict__ bstart)
