@@ -67,6 +67,9 @@ constexpr int kBuckets = 1 << (2 * kKeyBits);
 #ifndef LZ77_LINEAR_SCAN
 #define LZ77_LINEAR_SCAN 128
 #endif
+#ifndef LZ77_BUILD_ONLY
+#define LZ77_BUILD_ONLY 0  // (timing experiments) stage + build only, no parse: the output is invalid
+#endif
 #ifndef LZ77_DEFER_STORE
 #define LZ77_DEFER_STORE 1  // (token loop 2) store a token one pass later, behind the next token's loads
 #endif
@@ -492,55 +495,65 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
         const int rows = (bytes + kThreads - 1) / kThreads;  // rows of 32 positions per warp
         const int cbase = dst0 + warp * rows * 32;
         const int cend = min(dst0 + bytes, cbase + rows * 32);
+        // Counters: one 16-bit count per (bucket, warp); the word of (column, key) is
+        // cnt[col * kBuckets + key] with the even warp of the column in its low half -- the keys
+        // of a row spread over all banks (6.19 -> 6.00 ms against key-major words), and the scan
+        // below reads four keys per 128-bit load.  Measured and not kept: no atomics at all -- a
+        // warp owns its counters, so the first lane of every group of equal keys (a second
+        // MATCH.ANY per row) can add with a plain load and store -- 7.36 ms: MATCH.ANY, about 55
+        // cycles of its unit per row, is the build's bottleneck, not ATOMS; ranks from eleven
+        // ballots instead of MATCH.ANY build faster alone (2.2 vs 2.9 ms) but take issue slots
+        // from the tiles that are parsing: 6.42 ms.
         for (int i = cbase + lane; i < cend; i += 32)
-            atomicAdd(&cnt[bucket_key(smem, i) * (kWarps / 2) + cnt_col], 1u << cnt_sh);
+            atomicAdd(&cnt[cnt_col * kBuckets + bucket_key(smem, i)], 1u << cnt_sh);
         __syncthreads();
         {
             // thread t owns buckets [t*per, (t+1)*per): exclusive scan across the
             // warps' counters, then across buckets
             constexpr int per = kBuckets / kThreads;
-            uint32_t tot[per];
-            uint32_t sum = 0;
+            static_assert(per == 4, "four buckets per thread: one 128-bit load per counter column");
+            uint32_t tot[per] = {0u, 0u, 0u, 0u};
+            uint32_t x[kWarps / 2][per];  // exclusive offsets of the column's two warps, packed
+#pragma unroll
+            for (int w = 0; w < kWarps / 2; w++) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(cnt + w * kBuckets + threadIdx.x * per);
+                const uint32_t vv[per] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int b = 0; b < per; b++) {
+                    const uint32_t lo = vv[b] & 0xffffu, hi = vv[b] >> 16;
+                    x[w][b] = tot[b] | ((tot[b] + lo) << 16);
+                    tot[b] += lo + hi;
+                }
+            }
+            const uint32_t sum = tot[0] + tot[1] + tot[2] + tot[3];
+            uint32_t base = block_exclusive_scan_u32<kThreads>(sum, s_warp, &s_total);
+            uint32_t first[per];
 #pragma unroll
             for (int b = 0; b < per; b++) {
-                uint32_t *c = cnt + (threadIdx.x * per + b) * (kWarps / 2);
-                uint32_t run = 0;
-#pragma unroll
-                for (int w = 0; w < kWarps / 2; w++) {
-                    const uint32_t v = c[w];
-                    const uint32_t lo = v & 0xffffu, hi = v >> 16;
-                    c[w] = run | ((run + lo) << 16);
-                    run += lo + hi;
-                }
-                tot[b] = run;
-                sum += run;
-            }
-            uint32_t base = block_exclusive_scan_u32<kThreads>(sum, s_warp, &s_total);
-            if (kSent) {
-                // bucket k: sentinel at base + k, entries behind it; the start is folded into
-                // both halves of the warps' counters, so the scatter reads nothing else
-#pragma unroll
-                for (int b = 0; b < per; b++) {
-                    const uint32_t first = base + (uint32_t)(threadIdx.x * per + b) + 1u;
-                    sorted[first - 1u] = (PosT)0;
-                    uint32_t *c = cnt + (threadIdx.x * per + b) * (kWarps / 2);
-#pragma unroll
-                    for (int w = 0; w < kWarps / 2; w++) c[w] += first * 0x10001u;
-                    base += tot[b];
-                }
-            } else {
-#pragma unroll
-                for (int b = 0; b < per; b++) {
+                if (kSent) {
+                    // bucket k: sentinel at base + k, entries behind it; the start is folded
+                    // into the counters of all warps, so the scatter reads nothing else
+                    first[b] = base + (uint32_t)(threadIdx.x * per + b) + 1u;
+                    sorted[first[b] - 1u] = (PosT)0;
+                } else {
+                    first[b] = 0u;
                     bstart[threadIdx.x * per + b] = (PosT)base;
-                    base += tot[b];
                 }
-                if (threadIdx.x == kThreads - 1) bstart[kBuckets] = (PosT)base;
+                base += tot[b];
+            }
+            if (!kSent && threadIdx.x == kThreads - 1) bstart[kBuckets] = (PosT)base;
+#pragma unroll
+            for (int w = 0; w < kWarps / 2; w++) {
+                uint4 v;
+                v.x = x[w][0] + first[0] * 0x10001u, v.y = x[w][1] + first[1] * 0x10001u;
+                v.z = x[w][2] + first[2] * 0x10001u, v.w = x[w][3] + first[3] * 0x10001u;
+                *reinterpret_cast<uint4 *>(cnt + w * kBuckets + threadIdx.x * per) = v;
             }
         }
         __syncthreads();
-        // Every lane takes part -- a lane past the end with a key of its own -- because a
-        // shuffle under a partial mask costs a second MATCH.ANY, the slowest instruction
-        // of the build.  (kBatch rows can be issued together; one at a time is fastest.)
+        // Scatter, row by row.  Every lane takes part -- a lane past the end with a key of its
+        // own -- because a shuffle under a partial mask costs a second MATCH.ANY.  (kBatch rows
+        // can be issued together; one at a time is fastest.)
         constexpr int kBatch = LZ77_SCATTER_BATCH;
         for (int r0 = 0; r0 < rows; r0 += kBatch) {
             int key[kBatch];
@@ -573,12 +586,11 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
                 const int leader = __ffs(peers[b]) - 1;
                 uint32_t old = 0;
                 if (valid && lane == leader)
-                    old = atomicAdd(&cnt[key[b] * (kWarps / 2) + cnt_col],
-                                    (uint32_t)__popc(peers[b]) << cnt_sh);
+                    old = (atomicAdd(&cnt[cnt_col * kBuckets + key[b]], (uint32_t)__popc(peers[b]) << cnt_sh) >>
+                           cnt_sh) & 0xffffu;
                 old = __shfl_sync(0xffffffffu, old, leader);
                 if (valid) {
-                    const int slot = (kSent ? 0 : (int)bstart[key[b]]) + (int)((old >> cnt_sh) & 0xffffu) +
-                                     __popc(peers[b] & lt_mask);
+                    const int slot = (kSent ? 0 : (int)bstart[key[b]]) + (int)old + __popc(peers[b] & lt_mask);
                     sorted[slot] = (PosT)i;
                 }
             }
@@ -602,7 +614,7 @@ lz77_parse_bucket_kernel(const uint8_t *__restrict__ in, long long n, long long 
         const long long seg_lo =
             tile_lo + (long long)(warp * kSegsPerWarp + sg) * kSeg;
         const long long sgm = seg_lo / kSeg;  // global segment index
-        if (seg_lo < n) {
+        if (seg_lo < n && !LZ77_BUILD_ONLY) {
             long long seg_hi = seg_lo + kSeg;
             if (seg_hi > n) seg_hi = n;
             const int seg_end = (int)(seg_hi - src_lo) + dst0;
