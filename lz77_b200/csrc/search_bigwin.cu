@@ -50,6 +50,9 @@ __device__ __forceinline__ int big_key(uint32_t b0, uint32_t b1)
 #endif
 constexpr int kSortThreads = LZ77_SORT_THREADS;
 constexpr int kSortWarps = kSortThreads / 32;
+#ifndef LZ77_SORT_BALLOT
+#define LZ77_SORT_BALLOT 1
+#endif
 
 // ---------------------------------------------------------------------------
 // per-block stable sort of positions by key
@@ -96,7 +99,19 @@ __device__ __forceinline__ void radix_pass(uint32_t *dst, int n, uint32_t *cnt, 
         if (valid) {
             const uint32_t el = elem_of(i);
             const int d = digit_of(el);
+#if LZ77_SORT_BALLOT
+            // lanes with the same digit, from one ballot per digit bit: MATCH.ANY occupies its
+            // unit for ~55 cycles a row, and this kernel has issue slots to spare (17 % busy)
+            unsigned peers = vmask;
+#pragma unroll
+            for (int bit = 0; (1 << bit) < kBins; bit++) {
+                const bool one = (d >> bit) & 1;
+                const unsigned bal = __ballot_sync(vmask, one);
+                peers &= one ? bal : ~bal;
+            }
+#else
             const unsigned peers = __match_any_sync(vmask, d);
+#endif
             const int leader = __ffs(peers) - 1;
             uint32_t old = 0;
             if (lane == leader) old = atomicAdd(&cnt[warp * kBins + d], (uint32_t)__popc(peers));
