@@ -629,15 +629,30 @@ lz77_decode_tile_kernel(const uint32_t *__restrict__ words, long long n_words, l
                                 // source and destination do not overlap, at most 16 bytes:
                                 // five aligned words up front (one round of loads instead of
                                 // a load per byte), then predicated byte stores
+                                // (four bytes at a time, the next aligned word loaded only when
+                                // the match goes on: two thirds of the matches end within four
+                                // bytes, and sixteen predicated byte stores cost every pass ~80
+                                // instructions whatever the lengths)
                                 const volatile uint32_t *sw =
                                     reinterpret_cast<const volatile uint32_t *>(tile + (s_rel & ~3));
-                                const int sh = (s_rel & 3) * 8;
-                                const uint32_t a0 = sw[0], a1 = sw[1], a2 = sw[2], a3 = sw[3], a4 = sw[4];
-                                const uint32_t v[4] = {__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh),
-                                                       __funnelshift_r(a2, a3, sh), __funnelshift_r(a3, a4, sh)};
+                                const int sh = s_rel * 8;  // (the funnel shift wraps: bits 3..4 count)
+                                uint32_t lo = sw[0], hi = sw[1];
+                                uint32_t v = __funnelshift_r(lo, hi, sh);
+                                dst[0] = (uint8_t)v;  // (len >= 1 here)
+                                if (len > 1) dst[1] = (uint8_t)(v >> 8);
+                                if (len > 2) dst[2] = (uint8_t)(v >> 16);
+                                if (len > 3) dst[3] = (uint8_t)(v >> 24);
 #pragma unroll
-                                for (int i = 0; i < 16; i++)
-                                    if (i < len) dst[i] = (uint8_t)(v[i >> 2] >> ((i & 3) * 8));
+                                for (int c = 1; c < 4; c++) {
+                                    if (len <= 4 * c) break;
+                                    lo = hi, hi = sw[c + 1];
+                                    v = __funnelshift_r(lo, hi, sh);
+                                    uint8_t *d = dst + 4 * c;
+                                    d[0] = (uint8_t)v;
+                                    if (len > 4 * c + 1) d[1] = (uint8_t)(v >> 8);
+                                    if (len > 4 * c + 2) d[2] = (uint8_t)(v >> 16);
+                                    if (len > 4 * c + 3) d[3] = (uint8_t)(v >> 24);
+                                }
                             } else if (off >= len) {
                                 for (int i = 0; i < len; i++) dst[i] = src[i];
                             } else {

@@ -80,6 +80,23 @@ def test_encode_equals_specification(lz, orc, sb, la, kind, n):
     assert lz.decode(enc) == data
 
 
+@pytest.mark.parametrize("sb,la", [(1, 15), (1, 255), (2, 15), (3, 4)])
+@pytest.mark.parametrize("kind,n", [("zeros", 20_000), ("zipf_text", 70_001), ("random", 9_000)])
+def test_tiny_search_buffers_any_lookahead(lz, orc, sb, la, kind, n):
+    """SB = 1 has an empty usable window (bitof(1) = 0 offset bits: literals only) whatever
+    the lookahead; SB = 2, 3 reach one to three bytes back.  The token loop's "no candidate"
+    value (staged position 0) must lie in front of these windows too."""
+    from lz77_b200 import synth
+    data = synth.make(kind, n, seed=11).numpy().tobytes()
+    enc = lz.encode(data, la=la, sb=sb)
+    spec, ntok = _spec(orc, lz, data, sb, la)
+    assert enc == spec
+    if sb == 1:
+        assert ntok == n  # one literal token per byte
+    assert orc.decode(enc) == data
+    assert lz.decode(enc) == data
+
+
 @pytest.mark.parametrize("case", [c for c in GOLDEN_CASES if c.get("store")],
                          ids=lambda c: c["name"])
 def test_decode_reference_streams(lz, golden, case):
