@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """profiles/traffic.json from an `ncu --set full` capture of `bench.py` (the four main
 kernels of one device-resident step on the bench workload): DRAM bytes and executed warp
-instructions per launch, stamped with the hash of the kernel sources so that bench.py only
+instructions per step (summed over the launches of a kernel), stamped with the hash of the kernel sources so that bench.py only
 reports them while they describe the kernels that are running.
 
     python tools/make_traffic.py gpurun_out/rNN_bench_full.ncu-rep > profiles/traffic.json
@@ -34,14 +34,16 @@ def main():
         return int(v * scale)
 
     out = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum per "
-                       "launch, ncu --set full on `bench.py --steps 1 --warmup 3` (workload configs[1]); "
+                       "step (summed over the launches of a kernel), ncu --set full on `bench.py --steps 1 --warmup 3` (workload configs[1]); "
                        "bench.py reports them only while csrc_sha16 matches the kernel sources",
            "source": Path(rep).name, "workload_bytes": bench.WORKLOAD["n"],
            "csrc_sha16": bench.csrc_sha16()}
     for r in rows[2:]:
         k = r[name_i].split("(")[0].split("<")[0].replace("void ", "").replace("lz77::", "")
-        out[k] = to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr])
-        out[k + ".inst_executed"] = int(float(r[inst].replace(",", "")))
+        # (summed over the launches of the step: the encoder runs its input in pieces)
+        out[k] = out.get(k, 0) + to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr])
+        out[k + ".inst_executed"] = out.get(k + ".inst_executed", 0) + int(float(r[inst].replace(",", "")))
+        out[k + ".launches"] = out.get(k + ".launches", 0) + 1
     print(json.dumps(out, indent=1))
 
 
