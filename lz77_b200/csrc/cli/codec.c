@@ -27,11 +27,14 @@ struct bitFILE {
 };
 
 static int g_device = 0, g_gpus = 1, g_verbose = 0;
-static long g_piece_mib = 32, g_out_mib = 4096;
+/* pieces: 32 MiB of input per encode call; 4 MiB of stream per decode call -- the decoder's
+ * pinned buffers (stream piece + two output pieces) are a fixed cost of ~5 ms per 16 MiB
+ * pinned, and a 256 MiB file is decoded before three 70 MiB buffers are even registered */
+static long g_piece_mib = 32, g_dpiece_mib = 4, g_out_mib = 4096;
 
 void lz77_cli_set_device(int device) { g_device = device; }
 void lz77_cli_set_gpus(int n) { g_gpus = n < 1 ? 1 : n; }
-void lz77_cli_set_piece_mib(long mib) { g_piece_mib = mib < 1 ? 1 : mib; }
+void lz77_cli_set_piece_mib(long mib) { g_piece_mib = g_dpiece_mib = mib < 1 ? 1 : mib; }
 void lz77_cli_set_out_mib(long mib) { g_out_mib = mib < 1 ? 1 : mib; }
 void lz77_cli_set_verbose(int on) { g_verbose = on; }
 
@@ -571,16 +574,55 @@ static void wjob_submit(struct wjob *w, const unsigned char *p, long n)
  * its blocks (and keeps decoding block-parallel).  The decoded piece is written by a
  * second thread while the next piece is on the GPU (two output buffers).
  */
+/* the reader side of decode(): the next piece of the stream, read ahead on its own thread */
+struct dread {
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    FILE *f;
+    unsigned char *buf[2];
+    long off, cap; /* a piece lands at buf[i] + off, cap bytes at most */
+    long got[2];
+    int full[2], err;
+};
+
+static void *dread_main(void *arg)
+{
+    struct dread *d = arg;
+    int i = 0;
+    for (;;) {
+        long got;
+        int err;
+        pthread_mutex_lock(&d->mu);
+        while (d->full[i])
+            pthread_cond_wait(&d->cv, &d->mu);
+        pthread_mutex_unlock(&d->mu);
+        got = (long)fread(d->buf[i] + d->off, 1, (size_t)d->cap, d->f);
+        err = ferror(d->f);
+        memset(d->buf[i] + d->off + got, 0, 16);
+        pthread_mutex_lock(&d->mu);
+        d->got[i] = got;
+        d->err |= err;
+        d->full[i] = 1;
+        pthread_cond_broadcast(&d->cv);
+        pthread_mutex_unlock(&d->mu);
+        if (got < d->cap || err)
+            break; /* lz77.c:271-280: a short read ends the stream */
+        i ^= 1;
+    }
+    return NULL;
+}
+
 void decode(struct bitFILE *file, FILE *out)
 {
     unsigned char hdr[4];
-    unsigned char *raw, *sbuf = NULL, *obuf[2] = {NULL, NULL}, *hist;
-    long sbuf_cap = 0, obuf_cap[2] = {0, 0}, hist_len = 0, raw_cap, piece_tokens;
+    unsigned char *sbuf = NULL, *obuf[2] = {NULL, NULL}, *hist;
+    long sbuf_cap = 0, obuf_cap[2] = {0, 0}, hist_len = 0, raw_cap, piece_tokens, lead;
     long out_limit = g_out_mib << 20, total_in = 4, total_out = 0;
-    int sb, la, ob, lb, tbits, rc, last = 0, cur = 0;
+    int sb, la, ob, lb, tbits, rc, last = 0, cur = 0, slot = 0, aligned;
     long block;
     struct wjob w;
-    pthread_t writer;
+    struct dread rd;
+    pthread_t writer, reader;
     struct timespec t0, t1;
 
     bind_device();
@@ -596,16 +638,33 @@ void decode(struct bitFILE *file, FILE *out)
     ob = lz77_bitof(sb);
     lb = lz77_bitof(la);
     tbits = ob + lb + 8;
+    aligned = (tbits & 7) == 0;
     block = lz77_gpu_block_size(sb);
     /* whole tokens, a whole number of bytes */
-    piece_tokens = (piece_bytes() * 8 / tbits) & ~7L;
+    piece_tokens = ((g_dpiece_mib << 20) * 8 / tbits) & ~7L;
     if (piece_tokens < 8)
         piece_tokens = 8;
     raw_cap = piece_tokens / 8 * tbits;
-    raw = malloc((size_t)raw_cap + 16);
     hist = malloc((size_t)(2 * block));
-    if (raw == NULL || hist == NULL)
+    if (hist == NULL)
         die("allocating the input buffer", LZ77_E_NOMEM);
+    /* Byte-aligned tokens (both benchmark parameter sets): a piece is read straight into
+     * pinned memory behind a lead area, and the standalone stream of a library call --
+     * header, the retained tail as literal tokens, the piece's tokens -- is completed in
+     * place in FRONT of the tokens (the lead area, or tokens this piece has consumed):
+     * nothing is copied.  Other widths are assembled bit by bit in a second buffer. */
+    lead = aligned ? ((4 + 2 * block * (tbits >> 3) + 63) & ~63L) : 0;
+    memset(&rd, 0, sizeof rd);
+    pthread_mutex_init(&rd.mu, NULL);
+    pthread_cond_init(&rd.cv, NULL);
+    rd.f = file->file;
+    rd.off = lead;
+    rd.cap = raw_cap;
+    for (rc = 0; rc < 2; rc++) {
+        rd.buf[rc] = aligned ? lz77_gpu_host_alloc(lead + raw_cap + 64) : malloc((size_t)raw_cap + 64);
+        if (rd.buf[rc] == NULL)
+            die("allocating the input buffer", LZ77_E_NOMEM);
+    }
     memset(&w, 0, sizeof w);
     pthread_mutex_init(&w.mu, NULL);
     pthread_cond_init(&w.cv, NULL);
@@ -619,46 +678,63 @@ void decode(struct bitFILE *file, FILE *out)
     }
     pthread_create(&writer, NULL, wjob_main, &w);
     clock_gettime(CLOCK_MONOTONIC, &t0);
+    pthread_create(&reader, NULL, dread_main, &rd);
 
     while (!last) {
-        long got = (long)fread(raw, 1, (size_t)raw_cap, file->file);
-        long n_tok, cursor = 0;
-        if (ferror(file->file)) {
+        unsigned char *raw;
+        long got, n_tok, cursor = 0;
+        pthread_mutex_lock(&rd.mu);
+        while (!rd.full[slot])
+            pthread_cond_wait(&rd.cv, &rd.mu);
+        got = rd.got[slot];
+        rc = rd.err;
+        pthread_mutex_unlock(&rd.mu);
+        if (rc) {
             perror("Error reading bits"); /* lz77.c:273-277 */
             exit(EXIT_FAILURE);
         }
-        memset(raw + got, 0, 16);
+        raw = rd.buf[slot] + lead;
         total_in += got;
         last = got < raw_cap;
         /* lz77.c:271-280: a short read ends the stream, trailing bits < T are padding */
         n_tok = last ? (got * 8) / tbits : piece_tokens;
         while (cursor < n_tok) {
-            long take = n_tok - cursor, m = 0, need, bit;
+            long take = n_tok - cursor, m = 0, n_stream;
+            const unsigned char *stream;
             for (;;) {
-                need = 4 + ((hist_len + take) * tbits + 7) / 8 + 32;
-                if (need > sbuf_cap) {
-                    if (sbuf != NULL)
-                        lz77_gpu_host_free(sbuf);
-                    sbuf_cap = need + need / 4;
-                    sbuf = lz77_gpu_host_alloc(sbuf_cap);
-                    if (sbuf == NULL)
-                        die("allocating the input buffer", LZ77_E_NOMEM);
+                if (aligned) {
+                    const long tb = tbits >> 3;
+                    unsigned char *sp = raw + cursor * tb - hist_len * tb - 4;
+                    memcpy(sp, hdr, 4);
+                    memset(sp + 4, 0, (size_t)(hist_len * tb)); /* literal tokens: off 0, len 0 */
+                    put_literals(sp, 32, hist, hist_len, tbits, ob + lb);
+                    stream = sp;
+                    n_stream = 4 + (hist_len + take) * tb;
+                } else {
+                    const long need = 4 + ((hist_len + take) * tbits + 7) / 8 + 32;
+                    long bit = 32 + hist_len * tbits;
+                    if (need > sbuf_cap) {
+                        if (sbuf != NULL)
+                            lz77_gpu_host_free(sbuf);
+                        sbuf_cap = need + need / 4;
+                        sbuf = lz77_gpu_host_alloc(sbuf_cap);
+                        if (sbuf == NULL)
+                            die("allocating the input buffer", LZ77_E_NOMEM);
+                    }
+                    /* header, the tail as literal tokens, the piece's tokens */
+                    memcpy(sbuf, hdr, 4);
+                    memset(sbuf + 4, 0, (size_t)(need - 4)); /* bits are OR-ed in */
+                    put_literals(sbuf, 32, hist, hist_len, tbits, ob + lb);
+                    copy_bits(sbuf, bit, raw, cursor * tbits, take * tbits);
+                    bit += take * tbits;
+                    stream = sbuf;
+                    n_stream = (bit + 7) / 8;
                 }
-                /* header, the tail as literal tokens, the piece's tokens */
-                memcpy(sbuf, hdr, 4);
-                bit = 32 + hist_len * tbits;
-                if ((tbits & 7) != 0)
-                    memset(sbuf + 4, 0, (size_t)(need - 4));   /* bits are OR-ed in */
-                else
-                    memset(sbuf + 4, 0, (size_t)(hist_len * (tbits >> 3)));  /* literal tokens */
-                put_literals(sbuf, 32, hist, hist_len, tbits, ob + lb);
-                copy_bits(sbuf, bit, raw, cursor * tbits, take * tbits);
-                bit += take * tbits;
                 if (obuf[cur] == NULL) {
                     /* first use of this buffer: size it from the piece's decoded size (one
                      * token scan) -- pinning memory twice costs far more */
                     long want = 0;
-                    rc = lz77_gpu_decode_size(sbuf, (bit + 7) / 8, &want);
+                    rc = lz77_gpu_decode_size(stream, n_stream, &want);
                     if (rc != LZ77_OK)
                         die("decoding", rc);
                     obuf_cap[cur] = want + want / 4 + (1L << 20);
@@ -668,7 +744,7 @@ void decode(struct bitFILE *file, FILE *out)
                     if (obuf[cur] == NULL)
                         die("allocating the output buffer", LZ77_E_NOMEM);
                 }
-                rc = codec_decode(sbuf, (bit + 7) / 8, obuf[cur], obuf_cap[cur] - 16, &m);
+                rc = codec_decode(stream, n_stream, obuf[cur], obuf_cap[cur] - 16, &m);
                 if (rc == LZ77_OK)
                     break;
                 if (rc != LZ77_E_SPACE)
@@ -700,7 +776,13 @@ void decode(struct bitFILE *file, FILE *out)
             cur ^= 1;
             cursor += take;
         }
+        pthread_mutex_lock(&rd.mu); /* the piece is consumed: its buffer may be read into again */
+        rd.full[slot] = 0;
+        pthread_cond_broadcast(&rd.cv);
+        pthread_mutex_unlock(&rd.mu);
+        slot ^= 1;
     }
+    pthread_join(reader, NULL);
     wjob_wait(&w);
     pthread_mutex_lock(&w.mu);
     w.quit = 1;
@@ -717,8 +799,13 @@ void decode(struct bitFILE *file, FILE *out)
                 total_in, total_out, s, s > 0 ? (double)total_out / s / 1e9 : 0.0, g_gpus,
                 g_gpus > 1 ? "s" : "");
     }
-    free(raw);
     free(hist);
+    for (rc = 0; rc < 2; rc++) {
+        if (aligned)
+            lz77_gpu_host_free(rd.buf[rc]);
+        else
+            free(rd.buf[rc]);
+    }
     if (sbuf != NULL)
         lz77_gpu_host_free(sbuf);
     if (obuf[0] != NULL)
@@ -727,6 +814,8 @@ void decode(struct bitFILE *file, FILE *out)
         lz77_gpu_host_free(obuf[1]);
     pthread_mutex_destroy(&w.mu);
     pthread_cond_destroy(&w.cv);
+    pthread_mutex_destroy(&rd.mu);
+    pthread_cond_destroy(&rd.cv);
     if (w.failed) {
         perror("Writing output file");
         exit(EXIT_FAILURE);
