@@ -321,3 +321,65 @@ def test_sharded_encode_world2_gloo(sb, la):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+# --------------------------------------------------------------------------- #
+# the command-line program's host logic on CPUs (no GPU): the unmodified CLI sources
+# linked against tests/cli_stand_in/stand_in.c, a stand-in for the library built from
+# the oracle (test infrastructure; the product never links it)
+# --------------------------------------------------------------------------- #
+
+@pytest.fixture(scope="module")
+def cli_on_cpu(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli_stand_in")
+    inc = ["-I", str(ROOT / "include"), "-I", str(ROOT / "oracle")]
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", *inc, "-o", str(d / "liblz77b200.so"),
+                    str(ROOT / "tests" / "cli_stand_in" / "stand_in.c"),
+                    str(ROOT / "oracle" / "lz77_oracle.c"), "-lm"], check=True)
+    cli_src = ROOT / "lz77_b200" / "csrc" / "cli"
+    subprocess.run(["gcc", "-O2", "-std=gnu11", "-I", str(ROOT / "include"), "-o", str(d / "lz77"),
+                    str(cli_src / "lz77_cli.c"), str(cli_src / "codec.c"), "-L", str(d),
+                    "-llz77b200", "-lpthread", "-Wl,-rpath," + str(d)], check=True)
+    return d / "lz77"
+
+
+@pytest.mark.parametrize("sb,la", [(4095, 15), (1000, 20), (65535, 255)])
+def test_cli_piece_logic_on_cpu(cli_on_cpu, orc, tmp_path, sb, la):
+    """codec.c without a GPU: the encoder's pieces give the stream of a single call; the
+    decoder's pieces (whole tokens, the output tail carried as literal tokens -- assembled
+    in place for byte-aligned tokens, bit by bit for the 23-bit token --, read-ahead and
+    writer threads, the smaller piece on LZ77_E_SPACE) reproduce the input from streams of
+    the block encoder and of the reference encoder (matches across every piece seam)."""
+    from lz77_b200 import synth
+    data = synth.zipf_text(1_300_001, seed=21).numpy().tobytes() + bytes(700_000)
+    fin, one, pieces, back = (tmp_path / n for n in ("in.bin", "one.lz", "pieces.lz", "back.bin"))
+    fin.write_bytes(data)
+    args = ["-s", str(sb), "-l", str(la)]
+    subprocess.run([str(cli_on_cpu), "-c", "-i", str(fin), "-o", str(one), *args], check=True)
+    subprocess.run([str(cli_on_cpu), "-c", "-i", str(fin), "-o", str(pieces), "-p", "1", *args],
+                   check=True)
+    assert pieces.read_bytes() == one.read_bytes()
+    assert orc.decode(one.read_bytes()) == data
+    ref = tmp_path / "ref.lz"
+    ref.write_bytes(orc.ref_encode(data[:900_000], sb, la))
+    for stream, expect in ((one, data), (ref, data[:900_000])):
+        for extra in ([], ["-p", "1"], ["-p", "1", "-m", "1"]):
+            back.unlink(missing_ok=True)
+            subprocess.run([str(cli_on_cpu), "-d", "-i", str(stream), "-o", str(back), *extra],
+                           check=True)
+            assert back.read_bytes() == expect, (stream.name, extra)
+
+
+def test_cli_edge_files_on_cpu(cli_on_cpu, tmp_path):
+    """Empty and tiny files, and a stream cut in the middle of a token (lz77.c:271-280: the
+    trailing bits are padding) through the piece logic."""
+    for name, data in (("empty", b""), ("one", b"a"), ("abc", b"abcabcabcabcX")):
+        fin, enc, back = tmp_path / f"{name}.bin", tmp_path / f"{name}.lz", tmp_path / f"{name}.out"
+        fin.write_bytes(data)
+        subprocess.run([str(cli_on_cpu), "-c", "-i", str(fin), "-o", str(enc)], check=True)
+        subprocess.run([str(cli_on_cpu), "-d", "-i", str(enc), "-o", str(back)], check=True)
+        assert back.read_bytes() == data
+    cut = tmp_path / "cut.lz"
+    cut.write_bytes((tmp_path / "abc.lz").read_bytes()[:-1])
+    subprocess.run([str(cli_on_cpu), "-d", "-i", str(cut), "-o", str(tmp_path / "cut.out")], check=True)
+    assert b"abcabcabcabcX".startswith((tmp_path / "cut.out").read_bytes())
