@@ -1030,9 +1030,10 @@ cudaError_t launch_parse_bucket(const uint8_t *d_in, long long n_in, long long p
 {
     constexpr int kW = LZ77_PARSE_WARPS, kL = LZ77_PARSE_LANES;
     const bool small_la = P.la <= 16;
-    // (at least 16: staged position 0 then lies in front of every window -- the token loop's
-    // "no candidate" value -- also for SB = 1, whose usable window is empty)
-    const int hist_cap = P.window > 0 ? (P.window + 15) & ~15 : 16;
+    // (strictly more than the window: staged position 0 -- the token loop's "no candidate"
+    // value and the bucket lists' sentinel -- then lies in front of every window, also when
+    // the window is a multiple of 16 bytes and for SB = 1, whose usable window is empty)
+    const int hist_cap = (P.window & ~15) + 16;
     const long long tile_bytes = (long long)kW * (32 / kL) * kSegBytes;
     const long long n_tiles = (n_in + tile_bytes - 1) / tile_bytes;
     if (n_tiles == 0) return cudaSuccess;

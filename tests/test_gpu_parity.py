@@ -97,6 +97,22 @@ def test_tiny_search_buffers_any_lookahead(lz, orc, sb, la, kind, n):
     assert lz.decode(enc) == data
 
 
+@pytest.mark.parametrize("sb,la", [(48, 15), (1008, 16), (4080, 15), (8176, 4)])
+@pytest.mark.parametrize("kind,n", [("zipf_text", 70_001), ("zeros", 40_000), ("random", 30_000)])
+def test_windows_of_whole_16_byte_units(lz, orc, sb, la, kind, n):
+    """Search buffers that are a multiple of 16 bytes (and not a power of two, so the usable
+    window is SB itself): the staged history then fills its aligned area completely, and
+    the oldest byte of a full window must still not sit at staged position 0 -- the value
+    that ends the candidate walk."""
+    from lz77_b200 import synth
+    data = synth.make(kind, n, seed=13).numpy().tobytes()
+    enc = lz.encode(data, la=la, sb=sb)
+    spec, _ = _spec(orc, lz, data, sb, la)
+    assert enc == spec
+    assert orc.decode(enc) == data
+    assert lz.decode(enc) == data
+
+
 @pytest.mark.parametrize("case", [c for c in GOLDEN_CASES if c.get("store")],
                          ids=lambda c: c["name"])
 def test_decode_reference_streams(lz, golden, case):
